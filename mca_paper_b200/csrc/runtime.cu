@@ -1,0 +1,51 @@
+#include "runtime.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace mca {
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached = n > 0 ? n : 148;
+  }
+  return cached;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
+                      uint32_t box_inner, uint32_t box_outer) {
+  auto fn = encode_fn();
+  if (fn == nullptr) return MCA_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (row_stride * 2) % 16 != 0) return MCA_ERR_ALIGN;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MCA_OK : MCA_ERR_CUDA;
+}
+
+}  // namespace mca
+
+extern "C" int mca_version(void) { return 100; }
+
+extern "C" int mca_gemm_effective_splits(int K, int k_splits) { return mca::gemm_effective_splits(K, k_splits); }

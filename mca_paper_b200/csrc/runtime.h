@@ -1,0 +1,29 @@
+// Host-side helpers shared by the launchers: device properties, TMA tensor-map encoding (driver entry point is
+// resolved through the runtime so the library never links libcuda directly), launch error mapping.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mca_b200.h"
+
+namespace mca {
+
+int num_sms();
+
+// 2-D bf16 tensor map, 128B swizzle, zero OOB fill. `inner` is the contiguous dimension (elements), `outer`
+// the strided one; `row_stride` in elements.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
+                      uint32_t box_inner, uint32_t box_outer);
+
+inline int gemm_effective_splits(int K, int k_splits) {
+  const int kb_total = (K + 63) / 64;
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > kb_total) k_splits = kb_total;
+  const int per = (kb_total + k_splits - 1) / k_splits;
+  return (kb_total + per - 1) / per;
+}
+
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? MCA_OK : MCA_ERR_CUDA; }
+
+}  // namespace mca
