@@ -9,6 +9,7 @@
  *     (a cudaStream_t passed as void*), so every call is CUDA-graph capturable
  *   - return value: MCA_OK or one of the MCA_ERR_* codes below
  *   - bf16 tensors are raw 16-bit storage (`void*`), fp32 tensors are `float*`
+ *   - token matrices are row-major [B*N, cols]: row = sample*N + position (the packed layout of model.py:464)
  */
 #ifndef MCA_B200_H
 #define MCA_B200_H
@@ -18,6 +19,8 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+#define MCA_MAX_MODALITIES 8
 
 enum {
   MCA_OK = 0,
@@ -37,6 +40,39 @@ enum {
   MCA_EPI_GEGLU_BWD = 4  /* acc = dL/dh, aux0 = u; out0(bf16) = dL/du */
 };
 
+/* ---- static attention schedule (host-built once from token_types / attn_mask, model.py:383-430) ---- */
+typedef struct { int start, len; } mca_attn_tile;                 /* a run of <=128 positions inside a sample */
+typedef struct { int tile, flags; } mca_attn_ref;                 /* flags bit0: tile holds disallowed pairs   */
+typedef struct { int start, len, kt_off, kt_cnt; } mca_attn_qtile; /* query tile + its slice of the ref list   */
+
+/* ---- weight pack / gradient unpack descriptor (state_dict layout <-> kernel layout) ---- */
+typedef struct {
+  long long src_off;      /* element offset in the flat fp32 parameter (or gradient) buffer */
+  long long dst_off;      /* element offset in the bf16 operand arena (or fp32 partial-gradient arena) */
+  int rows, cols;         /* source matrix shape */
+  int dst_ld;             /* row stride of the kernel-layout matrix */
+  int dst_row0;           /* first destination row */
+  int mode;               /* 0 identity rows, 1 GEGLU interleave: 64 value rows then 64 gate rows per 128 block */
+  int half;               /* rows in the value half (mode 1) */
+  float scale;            /* pack: multiplies weights; unpack: multiplies gradients */
+  int n_splits;           /* unpack: number of split-K slabs to sum */
+  long long split_stride; /* unpack: elements between slabs */
+} mca_pack_desc;
+
+/* ---- one contrastive pair of MCAPretrainingLoss (model.py:160-168,198-220) ---- */
+typedef struct {
+  int a_row, b_row;   /* rows of the pooled block [B,R,d] */
+  uint32_t all_mask;  /* modalities that must ALL be present for a sample to count */
+  uint32_t any_mask;  /* modalities of which at least one must be present (0 = no constraint) */
+  int is_fcl;         /* counted in 'fcl_loss' (1) or 'no-fcl_loss' (0), model.py:221-222 */
+} mca_loss_pair;
+
+typedef struct {
+  float lr, beta1, beta2, eps, weight_decay, max_norm; /* max_norm <= 0: no clipping */
+  int lr_mode;                                         /* 0 constant, 1 cosine with linear warm-up */
+  long long warmup_steps, total_steps;
+} mca_adamw_cfg;
+
 int mca_version(void);
 
 /* Dense contraction out[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
@@ -50,6 +86,89 @@ int mca_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, i
                   int N, int K, int k_splits, int mode, void* out0, long long ld0, void* out1, long long ld1,
                   const void* aux0, long long ldaux, const float* bias, float alpha, void* stream);
 int mca_gemm_effective_splits(int K, int k_splits);
+
+/* Modality-dropout / pad-mask builder (model.py:455-466; collator masks encoders.py:307,339).  masks_host[m] is the
+ * DEVICE pointer of modality m's attention_mask [B, len m] (elem size 1 = bool, 8 = int64; non-zero = padded).
+ * Outputs: padding [B,N] bytes (== reference `padding`), pad_mod (per-modality [B,len] bytes, modality-major),
+ * present [B,n_mod] (== modality_sample_mask, model.py:458), live_count [B,n_mod], live_idx [B,N] (packed varlen
+ * gather indices: live positions of each modality in order, -1 filled), cu_live [B*n_mod+1] (exclusive cumsum),
+ * kt_class [B,n_kt] (0 all keys live, 1 mixed, 2 all padded -> tile skipped), any_absent (1 int). */
+int mca_build_offsets(const void* const* masks_host, const int* elem_sizes_host, const int* lens_host, int n_mod,
+                      int B, int N, const int* kt_start, const int* kt_len, int n_kt, uint8_t* padding,
+                      uint8_t* pad_mod, uint8_t* present, int* live_count, int* live_idx, int* cu_live,
+                      uint8_t* kt_class, int* any_absent, void* stream);
+
+/* LayerNorm over d = 512 (model.py:24-31; eps 1e-5).  Optional: pad [rows] bytes -> zero output (encoders.py:205),
+ * pe [seg_len,512] added after (encoders.py:208-209), row scatter out_row = (r/seg_len)*out_rows_per_b + out_row_off
+ * + r%seg_len (writes straight into the packed token buffer).  stats = (mean, rstd) per row. */
+int mca_layernorm512_fwd(const float* x, const float* gamma, const float* beta, float* y32, void* y16, float* stats,
+                         const uint8_t* pad, const float* pe, int seg_len, int out_rows_per_b, int out_row_off,
+                         long long rows, void* stream);
+int mca_layernorm512_bwd(const float* dy, const float* x, const float* stats, const float* gamma, float* dx32,
+                         void* dx16, float* dgamma, float* dbeta, const uint8_t* pad, int seg_len, int out_rows_per_b,
+                         int out_row_off, long long rows, void* stream);
+/* Input LayerNorm of EmbeddedSequenceEncoder (encoders.py:189,199): y = bf16 GEMM operand zero-padded to kpad cols;
+ * sets *nonfinite_flag when any token is not finite (encoders.py:197-198). */
+int mca_layernorm_in_fwd(const float* x, const float* w, const float* b, const uint8_t* pad, void* y_bf16,
+                         float* stats, int width, int kpad, long long rows, int* nonfinite_flag, void* stream);
+int mca_layernorm_in_param_bwd(const float* dy, int ld_dy, const float* x, const float* stats, const uint8_t* pad,
+                               float* dw, float* db, int width, long long rows, void* stream);
+int mca_colsum(const float* a, int ld, float* out, int width, long long rows, void* stream);
+
+/* fp32 state_dict-layout weights -> bf16 kernel-layout operands, and the inverse for gradients. */
+int mca_pack_weights(const float* params, void* arena_bf16, const mca_pack_desc* descs_dev, int n_desc, void* stream);
+int mca_unpack_grads(float* grads, const float* partials, const mca_pack_desc* descs_dev, int n_desc, void* stream);
+
+/* fusion tokens: broadcast into the packed buffer (model.py:460-461) / batch-sum of their gradient */
+int mca_broadcast_rows(const float* src, float* dst, int F, int d, int B, int rows_per_b, int row_off, void* stream);
+int mca_batchsum_rows(const float* src, float* out, int F, int d, int B, int rows_per_b, int row_off, int accumulate,
+                      void* stream);
+int mca_cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
+                      void* stream);
+
+/* Block-sparse masked multi-head attention (model.py:85-100), dim_head = 64.  qkv: bf16 [B*N, 3*H*64] = (Q*scale | K | V),
+ * out: bf16 [B*N, H*64], lse: [B,H,N] natural-log row log-sum-exp (+inf marks a fully masked row). */
+int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int n_qt, const mca_attn_ref* kt_list,
+                 const mca_attn_tile* k_tiles, int n_kt, const uint32_t* rowbits, const uint8_t* keygrp,
+                 const uint8_t* padding, const uint8_t* kt_class, const int* any_absent, float* vmean, void* out,
+                 float* lse, int B, int N, int H, void* stream);
+/* Backward: dout bf16 [B*N, H*64] -> dqkv bf16 [B*N, 3*H*64].  k_tiles_q lists, for every key tile, the query tiles
+ * that attend it (transposed schedule).  dq_accum: fp32 [B*N, H*64] scratch, delta: [B,H,N], ucorr: [B, H*64]. */
+int mca_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const mca_attn_qtile* k_tiles_q,
+                 int n_kt, const mca_attn_ref* qt_list, const mca_attn_tile* q_tiles, int n_qt, const uint32_t* rowbits,
+                 const uint8_t* keygrp, const uint8_t* padding, const uint8_t* kt_class, float* delta, float* ucorr,
+                 float* dq_accum, void* dqkv, int B, int N, int H, void* stream);
+
+/* Attention pooling core (model.py:472-473): qp [R,H*64] fp32 scaled queries, kv bf16 [B*N, 2*H*64] (K|V),
+ * rowbits[R] allowed key groups per pooled row, probs [B,H,R,N] saved for the backward, out [B,R,H*64]. */
+int mca_pool_attn_fwd(const float* qp, const void* kv, const uint8_t* padding, const uint8_t* keygrp,
+                      const uint32_t* rowbits, float* probs, uint8_t* full_masked, float* out, int B, int H, int R,
+                      int N, void* stream);
+int mca_pool_attn_bwd(const float* dout, const float* qp, const void* kv, const float* probs,
+                      const uint8_t* full_masked, float* ds_scratch, void* dkv, float* dqp, int B, int H, int R, int N,
+                      void* stream);
+/* tiny fp32 GEMM with arbitrary strides: C[m,n] = alpha*sum_k A(m,k)B(n,k) (+C) (+add) — return-token projections */
+int mca_small_gemm_f32(const float* A, long long sam, long long sak, const float* Bm, long long sbn, long long sbk,
+                       float* C, long long ldc, const float* add, long long ldadd, int M, int N, int K, float alpha,
+                       int accumulate, void* stream);
+
+/* All-pairs temperature-scaled InfoNCE (model.py:196-232 + utils/contrastive_loss_with_temperature.py:71-100,187).
+ * pooled_all: [GB, R, d] all-gathered pooled tokens, local rows at rank*B; losses[n_pairs] (NaN = no selected row);
+ * summary = {loss, fcl_loss, no-fcl_loss, #non-NaN}; w_default[p] = d loss / d losses[p]. */
+int mca_contrastive_allpairs_fwd(const float* pooled_all, const uint8_t* present, const mca_loss_pair* plan_dev,
+                                 int n_pairs, float* logit_scale, int B, int GB, int R, int d, int n_mod, int rank,
+                                 float scale_min, float scale_max, float* losses, float* summary, float* w_default,
+                                 void* stream);
+/* dpooled_all [GB,R,d] and dscale must be zeroed by the caller; w[p] = upstream gradient of losses[p]. */
+int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8_t* present, const mca_loss_pair* plan_dev,
+                                 int n_pairs, float* logit_scale, int B, int GB, int R, int d, int n_mod, int rank,
+                                 const float* w, float* dpooled_all, float* dscale, void* stream);
+
+/* clip_grad_norm_(max_norm) + AdamW + LR schedule on flat buffers (train_accel_gpu.py:80-86,116-119).
+ * step_dev: device int64 step counter (incremented here); grads are multiplied by grad_scale first (1/world). */
+int mca_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                        double* sumsq_scratch, long long* step_dev, float* total_norm_out, float grad_scale,
+                        const mca_adamw_cfg* cfg_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,247 @@
+// All-pairs temperature-scaled InfoNCE, forward and analytic backward, one CTA per contrastive pair.
+// Replaces the Python loop MCAPretrainingLoss.forward (model.py:196-232) and, per pair,
+// ContrastiveLossWithTemperature (utils/contrastive_loss_with_temperature.py:71-100,187): in-place clamp of
+// logit_scale, T = exp(s), logits_a = a b_all^T T, logits_b = b a_all^T T, rows selected by the presence mask,
+// labels = B*rank + i, (CE_a + CE_b)/2, NaN when no row is selected, then the NaN-aware mean of model.py:221-232 —
+// with zero host synchronisations (the reference does one .item() per pair, model.py:225).
+// `pooled_all` is the all-gathered [G*B, R, d] block; gradients are produced for every gathered row so the host can
+// reduce-scatter them (the autograd of torch.distributed.nn.functional.all_gather, utils/distributed.py:45-46).
+#include <math_constants.h>
+
+#include "mca_b200.h"
+#include "ptx.cuh"
+#include "runtime.h"
+
+namespace mca {
+
+constexpr int LOSS_THREADS = 256;
+
+struct LossArgs {
+  const float* pooled_all;  // [GB, R, d]
+  const uint8_t* present;   // [B, n_mod] local
+  const mca_loss_pair* plan;
+  float* logit_scale;
+  int B, GB, R, d, n_mod, rank, n_pairs;
+};
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ bool row_selected(const LossArgs& a, const mca_loss_pair& p, int i) {
+  unsigned bits = 0;
+  for (int m = 0; m < a.n_mod; ++m) bits |= (a.present[i * a.n_mod + m] ? 1u : 0u) << m;
+  if ((bits & p.all_mask) != p.all_mask) return false;
+  if (p.any_mask != 0 && (bits & p.any_mask) == 0) return false;
+  return true;
+}
+
+// logits into smem: la[i*GB + j], lb[i*GB + j]
+__device__ void compute_logits(const LossArgs& a, const mca_loss_pair& p, float T, float* la, float* lb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int total = 2 * a.B * a.GB;
+  for (int t = warp; t < total; t += nwarps) {
+    const int dir = t / (a.B * a.GB);
+    const int i = (t / a.GB) % a.B, j = t % a.GB;
+    const int rq = dir == 0 ? p.a_row : p.b_row, rk = dir == 0 ? p.b_row : p.a_row;
+    const float* q = a.pooled_all + (static_cast<long long>(a.rank * a.B + i) * a.R + rq) * a.d;
+    const float* k = a.pooled_all + (static_cast<long long>(j) * a.R + rk) * a.d;
+    float acc = 0.f;
+    for (int c = lane * 4; c < a.d; c += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(q + c);
+      const float4 y = *reinterpret_cast<const float4*>(k + c);
+      acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0) (dir == 0 ? la : lb)[i * a.GB + j] = acc * T;
+  }
+}
+
+__global__ void clamp_scale_kernel(float* s, float lo, float hi) {
+  if (threadIdx.x == 0) *s = fminf(fmaxf(*s, lo), hi);
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+loss_fwd_kernel(LossArgs a, float* __restrict__ losses) {
+  extern __shared__ float sm[];
+  float* la = sm;
+  float* lb = sm + a.B * a.GB;
+  __shared__ float s_sum[2];
+  __shared__ int s_cnt;
+  const mca_loss_pair p = a.plan[blockIdx.x];
+  const float T = expf(*a.logit_scale);
+  if (threadIdx.x == 0) s_sum[0] = 0.f, s_sum[1] = 0.f, s_cnt = 0;
+  compute_logits(a, p, T, la, lb);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int t = warp; t < 2 * a.B; t += nwarps) {
+    const int dir = t / a.B, i = t % a.B;
+    if (!row_selected(a, p, i)) continue;
+    const float* row = (dir == 0 ? la : lb) + i * a.GB;
+    float mx = -CUDART_INF_F;
+    for (int j = lane; j < a.GB; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max_f(mx);
+    float se = 0.f;
+    for (int j = lane; j < a.GB; j += 32) se += expf(row[j] - mx);
+    se = warp_sum_f(se);
+    if (lane == 0) {
+      const float ce = mx + logf(se) - row[a.rank * a.B + i];
+      atomicAdd(&s_sum[dir], ce);
+      if (dir == 0) atomicAdd(&s_cnt, 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    losses[blockIdx.x] = s_cnt == 0 ? CUDART_NAN_F : 0.5f * (s_sum[0] + s_sum[1]) / static_cast<float>(s_cnt);
+  }
+}
+
+// summary[0] = loss (model.py:224-232), [1] = fcl_loss, [2] = no-fcl_loss (model.py:221-222), [3] = #non-NaN;
+// w_default[p] = d loss / d loss_p
+__global__ void loss_reduce_kernel(const float* __restrict__ losses, const mca_loss_pair* __restrict__ plan, int P,
+                                   float* __restrict__ summary, float* __restrict__ w_default) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float tot = 0.f, fcl = 0.f, nofcl = 0.f;
+  int nv = 0, nf = 0, nn = 0;
+  for (int p = 0; p < P; ++p) {
+    float v = losses[p];
+    const bool isn = isnan(v);
+    if (!isn) ++nv;
+    if (isn) v = 0.f;
+    else if (isinf(v)) v = v > 0 ? 3.402823466e+38f : -3.402823466e+38f;
+    tot += v;
+    if (plan[p].is_fcl) fcl += v, ++nf;
+    else nofcl += v, ++nn;
+  }
+  summary[0] = nv == 0 ? tot : tot / static_cast<float>(nv);
+  summary[1] = nf > 0 ? fcl / nf : 0.f;
+  summary[2] = nn > 0 ? nofcl / nn : 0.f;
+  summary[3] = static_cast<float>(nv);
+  for (int p = 0; p < P; ++p) w_default[p] = (isnan(losses[p]) || nv == 0) ? 0.f : 1.0f / static_cast<float>(nv);
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+loss_bwd_kernel(LossArgs a, const float* __restrict__ w, float* __restrict__ dpooled_all, float* __restrict__ dscale) {
+  extern __shared__ float sm[];
+  float* la = sm;
+  float* lb = sm + a.B * a.GB;
+  __shared__ int s_cnt;
+  __shared__ float s_ds;
+  const mca_loss_pair p = a.plan[blockIdx.x];
+  const float wp = w[blockIdx.x];
+  if (wp == 0.f) return;
+  const float T = expf(*a.logit_scale);
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int i = 0; i < a.B; ++i) c += row_selected(a, p, i) ? 1 : 0;
+    s_cnt = c;
+    s_ds = 0.f;
+  }
+  compute_logits(a, p, T, la, lb);
+  __syncthreads();
+  if (s_cnt == 0) return;
+  const float gscale = wp * 0.5f / static_cast<float>(s_cnt);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // logits -> dL/dlogits in place; accumulate dL/ds = sum dlogit * logit
+  for (int t = warp; t < 2 * a.B; t += nwarps) {
+    const int dir = t / a.B, i = t % a.B;
+    float* row = (dir == 0 ? la : lb) + i * a.GB;
+    if (!row_selected(a, p, i)) {
+      for (int j = lane; j < a.GB; j += 32) row[j] = 0.f;
+      continue;
+    }
+    float mx = -CUDART_INF_F;
+    for (int j = lane; j < a.GB; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max_f(mx);
+    float se = 0.f;
+    for (int j = lane; j < a.GB; j += 32) se += expf(row[j] - mx);
+    se = warp_sum_f(se);
+    float ds = 0.f;
+    const int label = a.rank * a.B + i;
+    for (int j = lane; j < a.GB; j += 32) {
+      const float l = row[j];
+      const float g = gscale * (expf(l - mx) / se - (j == label ? 1.f : 0.f));
+      ds += g * l;
+      row[j] = g;
+    }
+    ds = warp_sum_f(ds);
+    if (lane == 0) atomicAdd(&s_ds, ds);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(dscale, s_ds);
+  // embedding gradients. dir 0: logits_a[i][j] = T a_i . b_all[j];  dir 1: logits_b[i][j] = T b_i . a_all[j]
+  for (int c = threadIdx.x; c < a.d; c += blockDim.x) {
+    for (int dir = 0; dir < 2; ++dir) {
+      const float* dl = dir == 0 ? la : lb;
+      const int rq = dir == 0 ? p.a_row : p.b_row, rk = dir == 0 ? p.b_row : p.a_row;
+      // d query_i += T sum_j dl[i][j] key_all[j]
+      for (int i = 0; i < a.B; ++i) {
+        float acc = 0.f;
+        for (int j = 0; j < a.GB; ++j)
+          acc += dl[i * a.GB + j] * a.pooled_all[(static_cast<long long>(j) * a.R + rk) * a.d + c];
+        if (acc != 0.f)
+          atomicAdd(dpooled_all + (static_cast<long long>(a.rank * a.B + i) * a.R + rq) * a.d + c, T * acc);
+      }
+      // d key_all[j] += T sum_i dl[i][j] query_i
+      for (int j = 0; j < a.GB; ++j) {
+        float acc = 0.f;
+        for (int i = 0; i < a.B; ++i)
+          acc += dl[i * a.GB + j] * a.pooled_all[(static_cast<long long>(a.rank * a.B + i) * a.R + rq) * a.d + c];
+        if (acc != 0.f) atomicAdd(dpooled_all + (static_cast<long long>(j) * a.R + rk) * a.d + c, T * acc);
+      }
+    }
+  }
+}
+
+}  // namespace mca
+
+using namespace mca;
+
+static int loss_smem_bytes(int B, int GB) { return 2 * B * GB * static_cast<int>(sizeof(float)); }
+
+extern "C" int mca_contrastive_allpairs_fwd(const float* pooled_all, const uint8_t* present,
+                                            const mca_loss_pair* plan_dev, int n_pairs, float* logit_scale, int B,
+                                            int GB, int R, int d, int n_mod, int rank, float scale_min,
+                                            float scale_max, float* losses, float* summary, float* w_default,
+                                            void* stream_) {
+  if (n_pairs <= 0 || B <= 0 || GB < B || (d % 4) != 0 || n_mod > MCA_MAX_MODALITIES) return MCA_ERR_SHAPE;
+  const int smem = loss_smem_bytes(B, GB);
+  if (smem > 96 * 1024) return MCA_ERR_SHAPE;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  clamp_scale_kernel<<<1, 32, 0, stream>>>(logit_scale, scale_min, scale_max);
+  LossArgs a{pooled_all, present, plan_dev, logit_scale, B, GB, R, d, n_mod, rank, n_pairs};
+  loss_fwd_kernel<<<n_pairs, LOSS_THREADS, smem, stream>>>(a, losses);
+  loss_reduce_kernel<<<1, 32, 0, stream>>>(losses, plan_dev, n_pairs, summary, w_default);
+  return check_launch();
+}
+
+extern "C" int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8_t* present,
+                                            const mca_loss_pair* plan_dev, int n_pairs, float* logit_scale, int B,
+                                            int GB, int R, int d, int n_mod, int rank, const float* w,
+                                            float* dpooled_all, float* dscale, void* stream_) {
+  if (n_pairs <= 0 || B <= 0 || GB < B || (d % 4) != 0) return MCA_ERR_SHAPE;
+  const int smem = loss_smem_bytes(B, GB);
+  if (smem > 96 * 1024) return MCA_ERR_SHAPE;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  LossArgs a{pooled_all, present, plan_dev, logit_scale, B, GB, R, d, n_mod, rank, n_pairs};
+  loss_bwd_kernel<<<n_pairs, LOSS_THREADS, smem, stream>>>(a, w, dpooled_all, dscale);
+  return check_launch();
+}

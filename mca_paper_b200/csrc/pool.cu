@@ -1,0 +1,286 @@
+// Attention pooling with R learned queries (model.py:472-473 -> Attention.forward model.py:73-105 with
+// context = final tokens, attn_mask = pool_mask, key_padding_mask = padding) and the tiny dense ops around it.
+// The R x N score block is small (R <= 32), so this is SIMT code bound by reading K/V once per (sample, head,
+// query) from L2; the expensive part of pooling (the K/V projection of all N tokens) runs on the tcgen05 GEMM.
+// Probabilities are materialised ([B,H,R,N] fp32, ~10 MB) so the backward is exact, including the reference's
+// fully-masked-row rule: -finfo.max fill makes such a row uniform 1/N over ALL keys, with no gradient to scores.
+#include <math_constants.h>
+
+#include "mca_b200.h"
+#include "ptx.cuh"
+#include "runtime.h"
+
+namespace mca {
+
+constexpr int DH = 64;
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < nw; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+__device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&v)[DH]) {
+  const uint4* p4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 q = p4[i];
+    v[8 * i + 0] = bf16_lo(q.x), v[8 * i + 1] = bf16_hi(q.x), v[8 * i + 2] = bf16_lo(q.y), v[8 * i + 3] = bf16_hi(q.y);
+    v[8 * i + 4] = bf16_lo(q.z), v[8 * i + 5] = bf16_hi(q.z), v[8 * i + 6] = bf16_lo(q.w), v[8 * i + 7] = bf16_hi(q.w);
+  }
+}
+
+// grid = B*H*R, block 256.  qp [R, H*64] fp32 (already scaled), kv [B*N, 2*H*64] bf16 (K | V)
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ kv, const uint8_t* __restrict__ padding,
+                const uint8_t* __restrict__ keygrp, const uint32_t* __restrict__ rowbits, float* __restrict__ probs,
+                uint8_t* __restrict__ full_masked, float* __restrict__ out, int B, int H, int R, int N) {
+  extern __shared__ float sc[];  // [N]
+  __shared__ float q[DH];
+  __shared__ float red[8];
+  __shared__ float part[4][DH];
+  const int r = blockIdx.x % R, h = (blockIdx.x / R) % H, b = blockIdx.x / (R * H);
+  const int ld = 2 * H * DH;
+  if (threadIdx.x < DH) q[threadIdx.x] = qp[r * H * DH + h * DH + threadIdx.x];
+  __syncthreads();
+  const uint32_t bits = rowbits[r];
+  float mx = -CUDART_INF_F;
+  int n_allowed = 0;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const bool ok = ((bits >> keygrp[j]) & 1u) && padding[static_cast<long long>(b) * N + j] == 0;
+    float s = -CUDART_INF_F;
+    if (ok) {
+      float k[DH];
+      load_row64(kv + (static_cast<long long>(b) * N + j) * ld + h * DH, k);
+      s = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) s += q[c] * k[c];
+      ++n_allowed;
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_reduce(mx, red, true);
+  const float tot_allowed = block_reduce(static_cast<float>(n_allowed), red, false);
+  float* prow = probs + (static_cast<long long>(b * H + h) * R + r) * N;
+  if (tot_allowed == 0.f) {
+    // every key masked: softmax of a constant row = 1/N over all N keys (padded and disallowed ones included)
+    const float u = 1.0f / static_cast<float>(N);
+    for (int j = threadIdx.x; j < N; j += blockDim.x) sc[j] = u, prow[j] = u;
+    if (threadIdx.x == 0 && h == 0) full_masked[b * R + r] = 1;
+  } else {
+    float se = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const float e = sc[j] == -CUDART_INF_F ? 0.f : expf(sc[j] - mx);
+      sc[j] = e;
+      se += e;
+    }
+    se = block_reduce(se, red, false);
+    const float inv = 1.0f / se;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const float p = sc[j] * inv;
+      sc[j] = p;
+      prow[j] = p;
+    }
+    if (threadIdx.x == 0 && h == 0) full_masked[b * R + r] = 0;
+  }
+  __syncthreads();
+  // out[b, r, h*64 + c] = sum_j p[j] * V[b, j, h, c]
+  const int c = threadIdx.x % DH, grp = threadIdx.x / DH;
+  float acc = 0.f;
+  for (int j = grp; j < N; j += 4) {
+    const float p = sc[j];
+    if (p != 0.f) acc += p * __bfloat162float(kv[(static_cast<long long>(b) * N + j) * ld + H * DH + h * DH + c]);
+  }
+  part[grp][c] = acc;
+  __syncthreads();
+  if (threadIdx.x < DH)
+    out[(static_cast<long long>(b) * R + r) * H * DH + h * DH + threadIdx.x] =
+        part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+}
+
+// dS (written over `probs_to_ds` copy): grid = B*H*R.  dout [B, R, H*64] fp32.
+__global__ void __launch_bounds__(256)
+pool_bwd_scores_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ kv,
+                       const float* __restrict__ probs, const uint8_t* __restrict__ full_masked,
+                       float* __restrict__ ds, int B, int H, int R, int N) {
+  extern __shared__ float dp[];  // [N]
+  __shared__ float g[DH];
+  __shared__ float red[8];
+  const int r = blockIdx.x % R, h = (blockIdx.x / R) % H, b = blockIdx.x / (R * H);
+  const int ld = 2 * H * DH;
+  if (threadIdx.x < DH) g[threadIdx.x] = dout[(static_cast<long long>(b) * R + r) * H * DH + h * DH + threadIdx.x];
+  __syncthreads();
+  const float* prow = probs + (static_cast<long long>(b * H + h) * R + r) * N;
+  float* drow = ds + (static_cast<long long>(b * H + h) * R + r) * N;
+  if (full_masked[b * R + r]) {
+    for (int j = threadIdx.x; j < N; j += blockDim.x) drow[j] = 0.f;
+    return;
+  }
+  float dsum = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float p = prow[j];
+    float d = 0.f;
+    if (p != 0.f) {
+      float v[DH];
+      load_row64(kv + (static_cast<long long>(b) * N + j) * ld + H * DH + h * DH, v);
+#pragma unroll
+      for (int c = 0; c < DH; ++c) d += g[c] * v[c];
+    }
+    dp[j] = d;
+    dsum += p * d;
+  }
+  dsum = block_reduce(dsum, red, false);
+  for (int j = threadIdx.x; j < N; j += blockDim.x) drow[j] = prow[j] * (dp[j] - dsum);
+}
+
+// dK[b,j,h,:] = sum_r dS[b,h,r,j] qp[r,h,:] ; dV[b,j,h,:] = sum_r P[b,h,r,j] dout[b,r,h,:]   -> bf16 [B*N, 2*H*64]
+// grid = (ceil(N/64), H, B), block 256: thread = (key j_local = t%64, 16-wide dim group = t/64)
+__global__ void __launch_bounds__(256)
+pool_bwd_kv_kernel(const float* __restrict__ ds, const float* __restrict__ probs, const float* __restrict__ qp,
+                   const float* __restrict__ dout, __nv_bfloat16* __restrict__ dkv, int B, int H, int R, int N) {
+  extern __shared__ float sm[];  // qs[R][64], gs[R][64]
+  float* qs = sm;
+  float* gs = sm + R * DH;
+  const int h = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < R * DH; i += blockDim.x) {
+    const int r = i / DH, c = i % DH;
+    qs[i] = qp[r * H * DH + h * DH + c];
+    gs[i] = dout[(static_cast<long long>(b) * R + r) * H * DH + h * DH + c];
+  }
+  __syncthreads();
+  const int j = blockIdx.x * 64 + (threadIdx.x % 64);
+  const int c0 = (threadIdx.x / 64) * 16;
+  if (j >= N) return;
+  float ak[16], av[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ak[i] = 0.f, av[i] = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const long long o = (static_cast<long long>(b * H + h) * R + r) * N + j;
+    const float s = ds[o], p = probs[o];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ak[i] += s * qs[r * DH + c0 + i], av[i] += p * gs[r * DH + c0 + i];
+  }
+  const int ld = 2 * H * DH;
+  __nv_bfloat16* ok = dkv + (static_cast<long long>(b) * N + j) * ld + h * DH + c0;
+  __nv_bfloat16* ov = ok + H * DH;
+  uint4 q0, q1;
+  q0.x = pack_bf16x2(ak[0], ak[1]), q0.y = pack_bf16x2(ak[2], ak[3]), q0.z = pack_bf16x2(ak[4], ak[5]),
+  q0.w = pack_bf16x2(ak[6], ak[7]);
+  q1.x = pack_bf16x2(ak[8], ak[9]), q1.y = pack_bf16x2(ak[10], ak[11]), q1.z = pack_bf16x2(ak[12], ak[13]),
+  q1.w = pack_bf16x2(ak[14], ak[15]);
+  reinterpret_cast<uint4*>(ok)[0] = q0, reinterpret_cast<uint4*>(ok)[1] = q1;
+  q0.x = pack_bf16x2(av[0], av[1]), q0.y = pack_bf16x2(av[2], av[3]), q0.z = pack_bf16x2(av[4], av[5]),
+  q0.w = pack_bf16x2(av[6], av[7]);
+  q1.x = pack_bf16x2(av[8], av[9]), q1.y = pack_bf16x2(av[10], av[11]), q1.z = pack_bf16x2(av[12], av[13]),
+  q1.w = pack_bf16x2(av[14], av[15]);
+  reinterpret_cast<uint4*>(ov)[0] = q0, reinterpret_cast<uint4*>(ov)[1] = q1;
+}
+
+// dqp[r, h, :] = sum_b sum_j dS[b,h,r,j] K[b,j,h,:]   grid = H*R, block 256 (thread = (dim c = t%64, group t/64))
+__global__ void __launch_bounds__(256)
+pool_bwd_q_kernel(const float* __restrict__ ds, const __nv_bfloat16* __restrict__ kv, float* __restrict__ dqp, int B,
+                  int H, int R, int N) {
+  __shared__ float part[4][DH];
+  const int r = blockIdx.x % R, h = blockIdx.x / R;
+  const int c = threadIdx.x % DH, grp = threadIdx.x / DH;
+  const int ld = 2 * H * DH;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* drow = ds + (static_cast<long long>(b * H + h) * R + r) * N;
+    for (int j = grp; j < N; j += 4) {
+      const float s = drow[j];
+      if (s != 0.f) acc += s * __bfloat162float(kv[(static_cast<long long>(b) * N + j) * ld + h * DH + c]);
+    }
+  }
+  part[grp][c] = acc;
+  __syncthreads();
+  if (threadIdx.x < DH)
+    dqp[r * H * DH + h * DH + threadIdx.x] =
+        part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+}
+
+// ---- tiny fp32 GEMM: C[m,n] = alpha * sum_k A(m,k) B(n,k) (+ C if accumulate) (+ add[m,n]); arbitrary strides
+__global__ void __launch_bounds__(256)
+small_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm,
+                  long long sbn, long long sbk, float* __restrict__ C, long long ldc, const float* __restrict__ add,
+                  long long ldadd, int M, int N, int K, float alpha, int accumulate) {
+  __shared__ float As[16][17], Bs[16][17];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int am = blockIdx.y * 16 + ty, ak = k0 + tx;
+    As[ty][tx] = (am < M && ak < K) ? A[am * sam + ak * sak] : 0.f;
+    const int bn = blockIdx.x * 16 + ty, bk = k0 + tx;
+    Bs[ty][tx] = (bn < N && bk < K) ? Bm[bn * sbn + bk * sbk] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += As[ty][k] * Bs[tx][k];
+    __syncthreads();
+  }
+  if (m < M && n < N) {
+    float v = alpha * acc;
+    if (accumulate) v += C[m * ldc + n];
+    if (add != nullptr) v += add[m * ldadd + n];
+    C[m * ldc + n] = v;
+  }
+}
+
+}  // namespace mca
+
+using namespace mca;
+
+extern "C" int mca_pool_attn_fwd(const float* qp, const void* kv, const uint8_t* padding, const uint8_t* keygrp,
+                                 const uint32_t* rowbits, float* probs, uint8_t* full_masked, float* out, int B,
+                                 int H, int R, int N, void* stream) {
+  if (B <= 0 || R <= 0 || N <= 0 || N * 4 > 200 * 1024) return MCA_ERR_SHAPE;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(pool_bwd_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  pool_fwd_kernel<<<B * H * R, 256, N * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      qp, reinterpret_cast<const __nv_bfloat16*>(kv), padding, keygrp, rowbits, probs, full_masked, out, B, H, R, N);
+  return check_launch();
+}
+
+extern "C" int mca_pool_attn_bwd(const float* dout, const float* qp, const void* kv, const float* probs,
+                                 const uint8_t* full_masked, float* ds_scratch, void* dkv, float* dqp, int B, int H,
+                                 int R, int N, void* stream_) {
+  if (B <= 0 || R <= 0 || N <= 0 || N * 4 > 200 * 1024) return MCA_ERR_SHAPE;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pool_bwd_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  const __nv_bfloat16* kvb = reinterpret_cast<const __nv_bfloat16*>(kv);
+  pool_bwd_scores_kernel<<<B * H * R, 256, N * sizeof(float), stream>>>(dout, kvb, probs, full_masked, ds_scratch, B, H,
+                                                                        R, N);
+  dim3 g2((N + 63) / 64, H, B);
+  pool_bwd_kv_kernel<<<g2, 256, 2 * R * DH * sizeof(float), stream>>>(ds_scratch, probs, qp, dout,
+                                                                      reinterpret_cast<__nv_bfloat16*>(dkv), B, H, R, N);
+  pool_bwd_q_kernel<<<H * R, 256, 0, stream>>>(ds_scratch, kvb, dqp, B, H, R, N);
+  return check_launch();
+}
+
+extern "C" int mca_small_gemm_f32(const float* A, long long sam, long long sak, const float* Bm, long long sbn,
+                                  long long sbk, float* C, long long ldc, const float* add, long long ldadd, int M,
+                                  int N, int K, float alpha, int accumulate, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return MCA_ERR_SHAPE;
+  dim3 grid((N + 15) / 16, (M + 15) / 16);
+  small_gemm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, add,
+                                                                             ldadd, M, N, K, alpha, accumulate);
+  return check_launch();
+}

@@ -44,6 +44,21 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
   return r == CUDA_SUCCESS ? MCA_OK : MCA_ERR_CUDA;
 }
 
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
+                     uint32_t box_inner, uint32_t box_outer) {
+  auto fn = encode_fn();
+  if (fn == nullptr) return MCA_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (row_stride * 4) % 16 != 0) return MCA_ERR_ALIGN;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MCA_OK : MCA_ERR_CUDA;
+}
+
 }  // namespace mca
 
 extern "C" int mca_version(void) { return 100; }

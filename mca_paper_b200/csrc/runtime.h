@@ -16,6 +16,10 @@ int num_sms();
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
                       uint32_t box_inner, uint32_t box_outer);
 
+// same for fp32 tensors (box_inner * 4 bytes must be <= 128 for the 128B swizzle)
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
+                     uint32_t box_inner, uint32_t box_outer);
+
 inline int gemm_effective_splits(int K, int k_splits) {
   const int kb_total = (K + 63) / 64;
   if (k_splits < 1) k_splits = 1;

@@ -1,0 +1,151 @@
+"""Modality encoders with the reference's constructor surface and state_dict names (encoders.py:17-283).
+
+The modules only *hold* parameters/buffers (so checkpoints of the reference load unchanged); all arithmetic of the
+two encoder types the shipped configs use — EmbeddedSequenceEncoder (CMU) and TabularEncoder (TCGA) — runs in the
+fused CUDA path driven by mca_paper_b200.engine.Engine.encode(), which writes tokens straight into the packed
+[B, N, 512] buffer.  Calling an encoder on its own (`encoder(batch) -> (tokens, attention_mask)`, the reference's
+module-level contract) goes through the same kernels via a single-modality engine.  SequenceEncoder,
+SparseTabularEncoder and PatchEncoder (not exercised by any shipped config) keep the constructor /
+state_dict surface; their kernels are listed as next in DESIGN.md and calling them raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+
+class TokenEncoder(nn.Module):
+    """nn.Embedding holder (encoders.py:17-37): padding_idx row is zero and gets no gradient, max_norm=1.0 rows are
+    renormalised in place at every forward (done by mca_embedding_renorm)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: Optional[int] = None,
+                 max_norm: Optional[float] = 1.0, **kwargs):
+        super().__init__()
+        self.num_embeddings = num_embeddings
+        self.embedding = nn.Embedding(num_embeddings, embedding_dim, padding_idx=padding_idx, max_norm=max_norm)
+
+
+class ContinuousValueEncoder(nn.Module):
+    """Parameter holder for encoders.py:40-72."""
+
+    def __init__(self, d_model: int, dropout: float = 0.1, max_value: int = 512, padding_value=0.0, **kwargs):
+        super().__init__()
+        self.linear1 = nn.Linear(1, d_model)
+        self.linear2 = nn.Linear(d_model, d_model)
+        self.norm = nn.LayerNorm(d_model)
+        self.max_value = max_value
+        self.padding_value = padding_value
+
+
+class PositionalEncoder(nn.Module):
+    """Sinusoidal table as a persistent buffer `pe` (encoders.py:123-135)."""
+
+    def __init__(self, d_model: int, dropout: float = 0.1, max_len: int = 2048, **kwargs):
+        super().__init__()
+        position = torch.arange(max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(max_len, d_model)
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe)
+
+
+class _EncoderBase(nn.Module):
+    kind = ""
+
+    def _spec(self):
+        raise NotImplementedError
+
+    def forward(self, batch):
+        from .standalone import run_single_encoder
+
+        return run_single_encoder(self, batch)
+
+
+class EmbeddedSequenceEncoder(_EncoderBase):
+    """encoders.py:169-214.  token_encoder = Sequential(LayerNorm(in), Linear(in, 512), LayerNorm(512))."""
+    kind = "EmbeddedSequenceEncoder"
+
+    def __init__(self, input_size=128, embedding_dim=512, padding_idx=0, dropout=0.0, max_tokens=1024, **kwargs):
+        super().__init__()
+        self.input_size, self.embedding_dim, self.max_tokens = input_size, embedding_dim, max_tokens
+        self.token_encoder = nn.Sequential(nn.LayerNorm(input_size), nn.Linear(input_size, embedding_dim),
+                                           nn.LayerNorm(embedding_dim))
+        self.positional_encoder = PositionalEncoder(embedding_dim, dropout, max_tokens)
+
+    def _spec(self):
+        return {"type": self.kind, "input_size": self.input_size, "max_tokens": self.max_tokens}
+
+
+class TabularEncoder(_EncoderBase):
+    """encoders.py:75-96 (padding_idx=-1 flows into both the embedding and the value encoder's pad test)."""
+    kind = "TabularEncoder"
+
+    def __init__(self, num_embeddings=128, embedding_dim=512, padding_idx=-1, dropout=0.0, max_value=10000, **kwargs):
+        super().__init__()
+        self.num_embeddings, self.padding_idx, self.max_value = num_embeddings, padding_idx, max_value
+        self.register_buffer("index", torch.arange(num_embeddings))
+        self.token_encoder = TokenEncoder(num_embeddings, embedding_dim, padding_idx)
+        self.value_encoder = ContinuousValueEncoder(embedding_dim, dropout, max_value, padding_idx)
+
+    def _spec(self):
+        return {"type": self.kind, "num_embeddings": self.num_embeddings, "max_tokens": self.num_embeddings,
+                "max_value": self.max_value, "padding_idx": self.padding_idx}
+
+
+class SparseTabularEncoder(nn.Module):
+    """encoders.py:100-120 — surface only."""
+
+    def __init__(self, num_embeddings=36602, embedding_dim=512, padding_idx=0, dropout=0.0, max_value=10000, **kwargs):
+        super().__init__()
+        self.token_encoder = TokenEncoder(num_embeddings, embedding_dim, padding_idx)
+        self.value_encoder = ContinuousValueEncoder(embedding_dim, dropout, max_value, padding_idx)
+
+    def forward(self, batch):
+        raise NotImplementedError("SparseTabularEncoder has no sm_100a kernel yet (not used by any shipped config)")
+
+
+class SequenceEncoder(nn.Module):
+    """encoders.py:145-166 — surface only."""
+
+    def __init__(self, num_embeddings=36602, embedding_dim=512, padding_idx=0, dropout=0.0, max_tokens=1024, **kwargs):
+        super().__init__()
+        self.token_encoder = TokenEncoder(num_embeddings, embedding_dim, padding_idx)
+        self.positional_encoder = PositionalEncoder(embedding_dim, dropout, max_tokens)
+
+    def forward(self, batch):
+        raise NotImplementedError("SequenceEncoder has no sm_100a kernel yet (not used by any shipped config)")
+
+
+class PatchEncoder(nn.Module):
+    """encoders.py:217-274 ("matrix" mode) — surface only."""
+
+    def __init__(self, patch_size=(16, 16), mode="matrix", num_channels=0, embedding_dim=512, max_tokens=1024,
+                 dropout: float = 0.1, attn_mask=True, pad_token=-10000, **kwargs):
+        super().__init__()
+        assert mode in ["matrix", "image", "video"]
+        input_dim = 1
+        for p in patch_size:
+            input_dim *= p
+        if mode != "matrix":
+            input_dim *= num_channels
+        self.patch_size, self.mode, self.pad_token = patch_size, mode, -10000
+        self.batch_to_tokens = nn.Sequential(nn.Identity(), nn.LayerNorm(input_dim), nn.Linear(input_dim, embedding_dim),
+                                             nn.LayerNorm(embedding_dim))
+        self.register_buffer("index", torch.arange(max_tokens))
+        self.embedding = nn.Embedding(max_tokens, embedding_dim)
+
+    def forward(self, batch):
+        raise NotImplementedError("PatchEncoder has no sm_100a kernel yet (not used by any shipped config)")
+
+
+encoders_dict = {
+    "SequenceEncoder": SequenceEncoder,
+    "TabularEncoder": TabularEncoder,
+    "SparseTabularEncoder": SparseTabularEncoder,
+    "PatchEncoder": PatchEncoder,
+    "EmbeddedSequenceEncoder": EmbeddedSequenceEncoder,
+}

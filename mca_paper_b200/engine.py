@@ -1,0 +1,496 @@
+"""Kernel orchestration for the MCA/MMA hot path: owns the flat parameter/gradient buffers, the bf16 operand arena,
+the activation workspaces and the launch order of forward, backward and the fused optimiser step.
+
+Everything numerical happens in libmca_b200.so (include/mca_b200.h); this file only sequences launches on torch's
+current stream, so a whole step can be captured into a CUDA graph (no host synchronisation, no allocation after the
+first call).  Reference call stack being replaced: MCA.forward model.py:448-478 -> MCALayer.forward :117-122 ->
+Attention.forward :73-105 / FeedForward :35-54 -> MCAPretrainingLoss.forward :175-233, its autograd backward, and
+train_accel_gpu.py:112-119 (zero_grad, backward, clip_grad_norm_, AdamW.step, scheduler.step).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .ops import P, S, call
+from .plan import StaticPlan
+
+D = 512
+DH = 64
+ALIGN = 64  # elements; keeps every parameter 256-byte aligned inside the flat buffers
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Engine:
+    def __init__(self, model, plan: StaticPlan, depth: int, heads: int, ff_inner: int, batch_size: int):
+        self.model = model
+        self.plan = plan
+        self.depth, self.H, self.I = depth, heads, ff_inner
+        if heads * DH != D:
+            raise AssertionError("this build supports dim = heads*dim_head = 512 with dim_head = 64")
+        self.IP = _round_up(ff_inner, 128)
+        self.B = batch_size
+        self.N = plan.N
+        self.M = self.B * self.N
+        self.R = plan.R
+        self.device = None
+        self.world, self.rank, self.group = 1, 0, None
+        self._ws_ready = False
+        self._flat_ptrs = None
+        self.check_finite = True
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def _param_list(self):
+        return list(self.model.named_parameters())
+
+    def ensure_flat(self):
+        """(Re)build the flat fp32 parameter buffer when parameters are not (or no longer) views of it —
+        e.g. after model.to(device) or load_state_dict(assign=True)."""
+        params = self._param_list()
+        dev = params[0][1].device
+        if dev.type != "cuda":
+            raise _lib.MCAKernelError("mca_paper_b200 runs on CUDA only: move the model to a B200 (no CPU fallback)")
+        ptrs = tuple(p.data_ptr() for _, p in params)
+        if self._flat_ptrs == ptrs and self.device == dev:
+            return
+        offs, total = {}, 0
+        for name, p in params:
+            offs[name] = total
+            total += _round_up(p.numel(), ALIGN)
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        for name, p in params:
+            o = offs[name]
+            flat[o:o + p.numel()].copy_(p.detach().reshape(-1).to(torch.float32))
+            p.data = flat[o:o + p.numel()].view(p.shape)
+        self.flat, self.offs, self.n_flat = flat, offs, total
+        self.flat_grad = torch.zeros_like(flat)
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.total_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.device = dev
+        self._flat_ptrs = tuple(p.data_ptr() for _, p in params)
+        self._build_static(dev)
+        self._build_pack_descs(dev)
+        self._alloc_workspace(dev)
+
+    def pview(self, name):  # fp32 view of a parameter inside the flat buffer
+        p = dict(self._param_list())[name]
+        o = self.offs[name]
+        return self.flat[o:o + p.numel()].view(p.shape)
+
+    def gview(self, name):
+        p = dict(self._param_list())[name]
+        o = self.offs[name]
+        return self.flat_grad[o:o + p.numel()].view(p.shape)
+
+    # ------------------------------------------------------------------------------------------ static tables
+    def _build_static(self, dev):
+        pl = self.plan
+        t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.keygrp = t(pl.keygrp)
+        self.rowbits = t(pl.rowbits.view(np.int32))
+        self.pool_rowbits = t(pl.pool_rowbits.view(np.int32))
+        self.q_tiles = t(pl.q_tiles)
+        self.kt_list = t(pl.kt_list)
+        self.k_tiles = t(pl.tiles)
+        self.k_tiles_q = t(pl.k_tiles_q)
+        self.qt_list = t(pl.qt_list)
+        self.kt_start = t(pl.tiles[:, 0].copy())
+        self.kt_len = t(pl.tiles[:, 1].copy())
+        self.n_kt = int(pl.tiles.shape[0])
+        self.loss_plan = torch.from_numpy(pl.loss_plan.view(np.uint8).copy()).to(dev)
+
+    # ------------------------------------------------------------------------------------------ weight layouts
+    def _build_pack_descs(self, dev):
+        """bf16 operand arena (kernel layouts) and fp32 split-K partial arena for weight gradients."""
+        descs = np.zeros(0, dtype=ops.PACK_DESC_DTYPE)
+        rows: List[tuple] = []
+        self.w = {}    # name -> (arena offset, rows, ld)
+        self.gw = {}   # name -> (partial arena offset, splits, slab elements)
+        a_off, g_off = 0, 0
+
+        def add_matrix(key, shape, parts, tokens):
+            nonlocal a_off, g_off
+            r, c = shape
+            tiles = (r // 128) * ((c + 127) // 128)
+            splits = ops.effective_splits(tokens, max(1, min(16, 296 // max(1, tiles))))
+            self.w[key] = (a_off, r, c)
+            self.gw[key] = (g_off, splits, r * c)
+            for (pname, prow, pcol, row0, mode, half, scale) in parts:
+                rows.append((self.offs[pname], a_off, prow, pcol, c, row0, mode, half, scale, g_off, splits, r * c))
+            a_off += _round_up(r * c, 512)
+            g_off += _round_up(splits * r * c, 512)
+
+        I, IP, M = self.I, self.IP, self.M
+        for l in range(self.depth):
+            p = f"layers.{l}."
+            add_matrix(p + "qkv", (3 * D, D), [(p + "attn.to_q.weight", D, D, 0, 0, 0, DH ** -0.5),
+                                               (p + "attn.to_kv.weight", 2 * D, D, D, 0, 0, 1.0)], M)
+            add_matrix(p + "out", (D, D), [(p + "attn.to_out.weight", D, D, 0, 0, 0, 1.0)], M)
+            add_matrix(p + "ff1", (2 * IP, D), [(p + "ff.feedforward.0.weight", 2 * I, D, 0, 1, I, 1.0)], M)
+            add_matrix(p + "ff2", (D, IP), [(p + "ff.feedforward.2.weight", D, I, 0, 0, 0, 1.0)], M)
+        add_matrix("attn_pool.kv", (2 * D, D), [("attn_pool.to_kv.weight", 2 * D, D, 0, 0, 0, 1.0)], M)
+        self.enc_kpad = {}
+        for name, enc in zip(self.plan.names, self.model.encoder_specs):
+            pre = f"encoders.{name}."
+            L = enc["max_tokens"]
+            if enc["type"] == "EmbeddedSequenceEncoder":
+                kin = enc["input_size"]
+                kp = _round_up(kin, 64)
+                self.enc_kpad[name] = kp
+                add_matrix(pre + "proj", (D, kp), [(pre + "token_encoder.1.weight", D, kin, 0, 0, 0, 1.0)], self.B * L)
+            elif enc["type"] == "TabularEncoder":
+                add_matrix(pre + "proj", (D, D), [(pre + "value_encoder.linear2.weight", D, D, 0, 0, 0, 1.0)], self.B * L)
+        self.arena = torch.zeros(a_off, device=dev, dtype=torch.bfloat16)
+        self.garena = torch.zeros(g_off, device=dev, dtype=torch.float32)
+        pd = np.zeros(len(rows), dtype=ops.PACK_DESC_DTYPE)
+        ud = np.zeros(len(rows), dtype=ops.PACK_DESC_DTYPE)
+        for i, (src, aoff, prow, pcol, ld, row0, mode, half, scale, goff, splits, slab) in enumerate(rows):
+            pd[i] = (src, aoff, prow, pcol, ld, row0, mode, half, scale, 1, 0)
+            ud[i] = (src, goff, prow, pcol, ld, row0, mode, half, scale, splits, slab)
+        self.n_desc = len(rows)
+        self.pack_descs = torch.from_numpy(pd.view(np.uint8).copy()).to(dev)
+        self.unpack_descs = torch.from_numpy(ud.view(np.uint8).copy()).to(dev)
+
+    def W(self, key):  # bf16 kernel-layout weight
+        o, r, c = self.w[key]
+        return self.arena[o:o + r * c].view(r, c)
+
+    def GW(self, key):  # fp32 split-K partial slabs
+        o, s, slab = self.gw[key]
+        r, c = self.w[key][1], self.w[key][2]
+        return self.garena[o:o + s * slab].view(s, r, c), s
+
+    def pack_weights(self):
+        call("mca_pack_weights", P(self.flat), P(self.arena), P(self.pack_descs), self.n_desc, S())
+
+    # ------------------------------------------------------------------------------------------ workspaces
+    def _alloc_workspace(self, dev):
+        M, N, B, H, R, IP, L = self.M, self.N, self.B, self.H, self.R, self.IP, self.depth
+        f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        b16 = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+        u8 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.uint8)
+        i32 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.int32)
+        ws = {}
+        ws["xa"] = [f32(M, D) for _ in range(L + 1)]
+        ws["st1"] = [f32(M, 2) for _ in range(L)]
+        ws["st2"] = [f32(M, 2) for _ in range(L)]
+        ws["x1_16"] = [b16(M, D) for _ in range(L)]
+        ws["qkv"] = [b16(M, 3 * D) for _ in range(L)]
+        ws["ao"] = [b16(M, D) for _ in range(L)]
+        ws["lse"] = [f32(B, H, N) for _ in range(L)]
+        ws["x2"] = [f32(M, D) for _ in range(L)]
+        ws["x3_16"] = [b16(M, D) for _ in range(L)]
+        ws["u"] = [b16(M, 2 * IP) for _ in range(L)]
+        ws["h"] = [b16(M, IP) for _ in range(L)]
+        ws["x1_32"], ws["x3_32"] = f32(M, D), f32(M, D)
+        ws["stF"], ws["xf_16"], ws["kvp"] = f32(M, 2), b16(M, D), b16(M, 2 * D)
+        ws["qp"], ws["probs"], ws["fm"] = f32(R, D), f32(B, H, R, N), u8(B, R)
+        ws["po"], ws["pooled"] = f32(B, R, D), f32(B, R, D)
+        ws["vmean"] = torch.zeros(B, D, device=dev, dtype=torch.float32)
+        # offsets / masks
+        ws["padding"], ws["pad_mod"] = u8(B, N), u8(B * self.plan.n_tok)
+        ws["present"], ws["live_count"] = u8(B, self.plan.n_mod), i32(B, self.plan.n_mod)
+        ws["live_idx"], ws["cu_live"] = i32(B, N), i32(B * self.plan.n_mod + 1)
+        ws["kt_class"], ws["any_absent"], ws["nonfinite"] = u8(B, self.n_kt), i32(1), i32(1)
+        # encoders
+        ws["enc"] = {}
+        for name, enc in zip(self.plan.names, self.model.encoder_specs):
+            rows = B * enc["max_tokens"]
+            e = {"z": f32(rows, D), "st_out": f32(rows, 2)}
+            if enc["type"] == "EmbeddedSequenceEncoder":
+                kp = self.enc_kpad[name]
+                e.update(y=b16(rows, kp), st_in=f32(rows, 2), dz16=b16(rows, D), dz32=f32(rows, D), dy=f32(rows, kp))
+            else:
+                e.update(h1=b16(rows, D), vpad=u8(rows), dz16=b16(rows, D), dz32=f32(rows, D), dh1=f32(rows, D))
+            ws["enc"][name] = e
+        # loss
+        nP = self.plan.n_pairs
+        ws["losses"], ws["summary"], ws["w_default"] = f32(nP), f32(4), f32(nP)
+        # backward scratch
+        ws["dx_a"], ws["dx_b"], ws["d16"] = f32(M, D), f32(M, D), b16(M, D)
+        ws["du"], ws["dattn"], ws["dqkv"] = b16(M, 2 * IP), b16(M, D), b16(M, 3 * D)
+        ws["dq_acc"], ws["delta"], ws["ucorr"] = f32(M, D), f32(B, H, N), f32(B, D)
+        ws["dkvp"], ws["dxf"] = b16(M, 2 * D), f32(M, D)
+        ws["pool_ds"], ws["dqp"], ws["dpo"] = f32(B, H, R, N), f32(R, D), f32(B, R, D)
+        self.ws = ws
+        self._gather_ws = None
+        self._ws_ready = True
+
+    def set_distributed(self, world: int, rank: int, group=None):
+        self.world, self.rank, self.group = world, rank, group
+        self._gather_ws = None
+
+    def _gather_buffers(self):
+        if self._gather_ws is None:
+            GB = self.world * self.B
+            dev = self.device
+            self._gather_ws = {
+                "pooled_all": torch.zeros(GB, self.R, D, device=dev, dtype=torch.float32),
+                "dpooled_all": torch.zeros(GB, self.R, D, device=dev, dtype=torch.float32),
+                "dpooled": torch.zeros(self.B, self.R, D, device=dev, dtype=torch.float32),
+                "dscale": torch.zeros(1, device=dev, dtype=torch.float32),
+            }
+        return self._gather_ws
+
+    # ------------------------------------------------------------------------------------------ forward
+    def build_offsets(self, batch):
+        pl, ws = self.plan, self.ws
+        masks = [batch[n]["attention_mask"] for n in pl.names]
+        for m, L in zip(masks, pl.lengths):
+            if m.shape != (self.B, L):
+                raise AssertionError(f"attention_mask shape {tuple(m.shape)} != {(self.B, L)} (batch must equal batch_size, model.py:454)")
+        self._mask_keepalive = [m if m.is_contiguous() else m.contiguous() for m in masks]
+        n = pl.n_mod
+        ptrs = (ctypes.c_void_p * n)(*[m.data_ptr() for m in self._mask_keepalive])
+        es = (ctypes.c_int * n)(*[m.element_size() for m in self._mask_keepalive])
+        lens = (ctypes.c_int * n)(*pl.lengths)
+        call("mca_build_offsets", ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(es, ctypes.c_void_p),
+             ctypes.cast(lens, ctypes.c_void_p), n, self.B, self.N, P(self.kt_start), P(self.kt_len), self.n_kt,
+             P(ws["padding"]), P(ws["pad_mod"]), P(ws["present"]), P(ws["live_count"]), P(ws["live_idx"]),
+             P(ws["cu_live"]), P(ws["kt_class"]), P(ws["any_absent"]), S())
+
+    def _pad_mod(self, i):
+        pl = self.plan
+        o = pl.offsets[i] * self.B
+        return self.ws["pad_mod"][o:o + self.B * pl.lengths[i]]
+
+    def encode(self, batch):
+        """Encoders write straight into the packed token buffer xa[0] (no `pack` copy, model.py:464)."""
+        pl, ws = self.plan, self.ws
+        x0 = ws["xa"][0]
+        for i, (name, enc) in enumerate(zip(pl.names, self.model.encoder_specs)):
+            pre = f"encoders.{name}."
+            L = enc["max_tokens"]
+            rows = self.B * L
+            e = ws["enc"][name]
+            pad = self._pad_mod(i)
+            if enc["type"] == "EmbeddedSequenceEncoder":
+                tok = batch[name]["tokens"]
+                if tok.dtype != torch.float32 or not tok.is_contiguous():
+                    tok = tok.to(torch.float32).contiguous()
+                e["tokens"] = tok
+                kin, kp = enc["input_size"], self.enc_kpad[name]
+                call("mca_layernorm_in_fwd", P(tok), P(self.pview(pre + "token_encoder.0.weight")),
+                     P(self.pview(pre + "token_encoder.0.bias")), P(pad), P(e["y"]), P(e["st_in"]), kin, kp, rows,
+                     P(ws["nonfinite"]), S())
+                ops.gemm(e["y"], 0, self.W(pre + "proj"), 0, rows, D, kp, _lib.EPI_F32, e["z"],
+                         bias=self.pview(pre + "token_encoder.1.bias"))
+                ops.layernorm512_fwd(e["z"], self.pview(pre + "token_encoder.2.weight"),
+                                     self.pview(pre + "token_encoder.2.bias"), x0, None, e["st_out"], rows, pad=pad,
+                                     pe=self.model.encoders[name].positional_encoder.pe, seg_len=L,
+                                     out_rows_per_b=self.N, out_row_off=pl.offsets[i])
+            elif enc["type"] == "TabularEncoder":
+                vals = batch[name]["values"]
+                if vals.dtype != torch.float32 or not vals.is_contiguous():
+                    vals = vals.to(torch.float32).contiguous()
+                e["values"] = vals
+                emb = self.pview(pre + "token_encoder.embedding.weight")
+                call("mca_embedding_renorm", P(emb), L, D, 1.0, S())  # nn.Embedding(max_norm=1.0), in place
+                call("mca_tabular_fwd", P(vals), P(self.pview(pre + "value_encoder.linear1.weight")),
+                     P(self.pview(pre + "value_encoder.linear1.bias")), P(e["h1"]), P(e["vpad"]),
+                     float(enc.get("max_value", 10000)), float(enc.get("padding_idx", -1)), D, rows, S())
+                ops.gemm(e["h1"], 0, self.W(pre + "proj"), 0, rows, D, D, _lib.EPI_F32, e["z"],
+                         bias=self.pview(pre + "value_encoder.linear2.bias"))
+                ops.layernorm512_fwd(e["z"], self.pview(pre + "value_encoder.norm.weight"),
+                                     self.pview(pre + "value_encoder.norm.bias"), x0, None, e["st_out"], rows,
+                                     pad=e["vpad"], pe=emb, seg_len=L, out_rows_per_b=self.N, out_row_off=pl.offsets[i])
+            else:
+                raise NotImplementedError(f"{enc['type']} is not wired into the fused MCA path yet")
+        if pl.F:
+            call("mca_broadcast_rows", P(self.pview("fusion_tokens")), P(x0), pl.F, D, self.B, self.N, pl.n_tok, S())
+
+    def attention_fwd(self, qkv, out, lse):
+        ws = self.ws
+        call("mca_attn_fwd", P(qkv), P(self.q_tiles), int(self.q_tiles.shape[0]), P(self.kt_list), P(self.k_tiles),
+             self.n_kt, P(self.rowbits), P(self.keygrp), P(ws["padding"]), P(ws["kt_class"]), P(ws["any_absent"]),
+             P(ws["vmean"]), P(out), P(lse), self.B, self.N, self.H, S())
+
+    def trunk_forward(self, batch):
+        """encoders -> depth x [LN, QKV, attention, out-proj(+res), LN, FF1(GEGLU), FF2(+res)] -> LN -> pooling."""
+        ws, M, IP = self.ws, self.M, self.IP
+        ws["nonfinite"].zero_()
+        self.build_offsets(batch)
+        self.encode(batch)
+        for l in range(self.depth):
+            p = f"layers.{l}."
+            gamma, beta = self.pview(p + "norm.gamma"), self.model.layers[l].norm.beta
+            ops.layernorm512_fwd(ws["xa"][l], gamma, beta, ws["x1_32"], ws["x1_16"][l], ws["st1"][l], M)
+            ops.gemm(ws["x1_16"][l], 0, self.W(p + "qkv"), 0, M, 3 * D, D, _lib.EPI_BF16, ws["qkv"][l])
+            self.attention_fwd(ws["qkv"][l], ws["ao"][l], ws["lse"][l])
+            ops.gemm(ws["ao"][l], 0, self.W(p + "out"), 0, M, D, D, _lib.EPI_RESID, ws["x2"][l], aux0=ws["x1_32"], ldaux=D)
+            ops.layernorm512_fwd(ws["x2"][l], gamma, beta, ws["x3_32"], ws["x3_16"][l], ws["st2"][l], M)
+            ops.gemm(ws["x3_16"][l], 0, self.W(p + "ff1"), 0, M, 2 * IP, D, _lib.EPI_GEGLU, ws["h"][l], ld0=IP,
+                     out1=ws["u"][l], ld1=2 * IP)
+            ops.gemm(ws["h"][l], 0, self.W(p + "ff2"), 0, M, D, IP, _lib.EPI_RESID, ws["xa"][l + 1], aux0=ws["x3_32"],
+                     ldaux=D)
+        # final norm + attention pooling (model.py:470-473)
+        ops.layernorm512_fwd(ws["xa"][self.depth], self.pview("norm.gamma"), self.model.norm.beta, None, ws["xf_16"],
+                             ws["stF"], M)
+        ops.gemm(ws["xf_16"], 0, self.W("attn_pool.kv"), 0, M, 2 * D, D, _lib.EPI_BF16, ws["kvp"])
+        rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
+        ops.small_gemm(rt, D, 1, wq, D, 1, ws["qp"], D, self.R, D, D, alpha=DH ** -0.5)
+        call("mca_pool_attn_fwd", P(ws["qp"]), P(ws["kvp"]), P(ws["padding"]), P(self.keygrp), P(self.pool_rowbits),
+             P(ws["probs"]), P(ws["fm"]), P(ws["po"]), self.B, self.H, self.R, self.N, S())
+        # pooled[b, r] = po[b, r] Wo^T + return_tokens[r]
+        for b in range(self.B):
+            ops.small_gemm(ws["po"][b], D, 1, wo, D, 1, ws["pooled"][b], D, self.R, D, D, add=rt, ldadd=D)
+        return ws["pooled"]
+
+    def loss_forward(self, pooled):
+        """All-gather of the pooled block (one collective instead of 2 per pair) + fused all-pairs InfoNCE."""
+        ws, g = self.ws, self._gather_buffers()
+        if self.world > 1:
+            torch.distributed.all_gather_into_tensor(g["pooled_all"], pooled.contiguous(), group=self.group)
+            pooled_all = g["pooled_all"]
+        else:
+            pooled_all = pooled
+        self._pooled_all = pooled_all
+        s = self.pview("loss.loss_fn.logit_scale")
+        lf = self.model.loss.loss_fn
+        call("mca_contrastive_allpairs_fwd", P(pooled_all), P(ws["present"]), P(self.loss_plan), self.plan.n_pairs, P(s),
+             self.B, self.world * self.B, self.R, D, self.plan.n_mod, self.rank,
+             float(lf.logit_scale_min if lf.logit_scale_min is not None else -1e30),
+             float(lf.logit_scale_max if lf.logit_scale_max is not None else 1e30),
+             P(ws["losses"]), P(ws["summary"]), P(ws["w_default"]), S())
+        return ws["losses"], ws["summary"]
+
+    # ------------------------------------------------------------------------------------------ backward
+    def loss_backward(self, w):
+        """w[p] = dL/d losses[p].  Returns dL/d pooled [B,R,D] (after the reduce-scatter of gathered gradients)."""
+        ws, g = self.ws, self._gather_buffers()
+        GB = self.world * self.B
+        dall = g["dpooled_all"] if self.world > 1 else g["dpooled"]
+        dall.zero_()
+        g["dscale"].zero_()
+        s = self.pview("loss.loss_fn.logit_scale")
+        call("mca_contrastive_allpairs_bwd", P(self._pooled_all), P(ws["present"]), P(self.loss_plan), self.plan.n_pairs,
+             P(s), self.B, GB, self.R, D, self.plan.n_mod, self.rank, P(w), P(dall), P(g["dscale"]), S())
+        if self.world > 1:
+            torch.distributed.reduce_scatter_tensor(g["dpooled"], dall, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        self.gview("loss.loss_fn.logit_scale").add_(g["dscale"].view(()))
+        return g["dpooled"]
+
+    def _dw(self, key, dY, X, rows_w, cols_w, tokens):
+        """dW[rows_w, cols_w] = dY^T X over `tokens` rows, both operands consumed MN-major, split-K partial slabs."""
+        part, splits = self.GW(key)
+        ops.gemm(dY, 1, X, 1, rows_w, cols_w, tokens, _lib.EPI_F32, part, ld0=cols_w, k_splits=splits)
+
+    def trunk_backward(self, dpooled):
+        """Reverse of trunk_forward; parameter gradients land in self.flat_grad (state_dict layout)."""
+        ws, pl, M, IP, B, R, H, N = self.ws, self.plan, self.M, self.IP, self.B, self.R, self.H, self.N
+        rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
+        dp2 = dpooled.reshape(B * R, D)
+        po2 = ws["po"].view(B * R, D)
+        # pooled = po Wo^T + rt
+        call("mca_batchsum_rows", P(dp2), P(self.gview("return_tokens")), R, D, B, R, 0, 1, S())
+        ops.small_gemm(dp2, 1, D, po2, 1, D, self.gview("attn_pool.to_out.weight"), D, D, D, B * R)       # dWo = dp^T po
+        ops.small_gemm(dp2, D, 1, wo, 1, D, ws["dpo"].view(B * R, D), D, B * R, D, D)                        # dpo = dp Wo
+        call("mca_pool_attn_bwd", P(ws["dpo"]), P(ws["qp"]), P(ws["kvp"]), P(ws["probs"]), P(ws["fm"]), P(ws["pool_ds"]),
+             P(ws["dkvp"]), P(ws["dqp"]), B, H, R, N, S())
+        sc = DH ** -0.5
+        ops.small_gemm(ws["dqp"], 1, D, rt, 1, D, self.gview("attn_pool.to_q.weight"), D, D, D, R, alpha=sc)  # dWq
+        ops.small_gemm(ws["dqp"], D, 1, wq, 1, D, self.gview("return_tokens"), D, R, D, D, alpha=sc, accumulate=True)
+        # through the K/V projection and the final LayerNorm
+        ops.gemm(ws["dkvp"], 0, self.W("attn_pool.kv"), 1, M, D, 2 * D, _lib.EPI_F32, ws["dxf"])
+        self._dw("attn_pool.kv", ws["dkvp"], ws["xf_16"], 2 * D, D, M)
+        dx, dx_alt = ws["dx_a"], ws["dx_b"]
+        ops.layernorm512_bwd(ws["dxf"], ws["xa"][self.depth], ws["stF"], self.pview("norm.gamma"), dx, ws["d16"],
+                             self.gview("norm.gamma"), None, M)
+        for l in reversed(range(self.depth)):
+            p = f"layers.{l}."
+            gamma, dgamma = self.pview(p + "norm.gamma"), self.gview(p + "norm.gamma")
+            # x4 = h W2^T + x3 ; h = geglu(u) ; u = x3 W1^T
+            ops.gemm(ws["d16"], 0, self.W(p + "ff2"), 1, M, IP, D, _lib.EPI_GEGLU_BWD, ws["du"], ld0=2 * IP,
+                     aux0=ws["u"][l], ldaux=2 * IP)
+            self._dw(p + "ff2", ws["d16"], ws["h"][l], D, IP, M)
+            ops.gemm(ws["du"], 0, self.W(p + "ff1"), 1, M, D, 2 * IP, _lib.EPI_RESID, dx_alt, aux0=dx, ldaux=D)  # dx3
+            self._dw(p + "ff1", ws["du"], ws["x3_16"][l], 2 * IP, D, M)
+            ops.layernorm512_bwd(dx_alt, ws["x2"][l], ws["st2"][l], gamma, dx, ws["d16"], dgamma, None, M)       # dx2
+            # x2 = ao Wo^T + x1
+            ops.gemm(ws["d16"], 0, self.W(p + "out"), 1, M, D, D, _lib.EPI_BF16, ws["dattn"])
+            self._dw(p + "out", ws["d16"], ws["ao"][l], D, D, M)
+            self.attention_bwd(l)
+            ops.gemm(ws["dqkv"], 0, self.W(p + "qkv"), 1, M, D, 3 * D, _lib.EPI_RESID, dx_alt, aux0=dx, ldaux=D)  # dx1
+            self._dw(p + "qkv", ws["dqkv"], ws["x1_16"][l], 3 * D, D, M)
+            ops.layernorm512_bwd(dx_alt, ws["xa"][l], ws["st1"][l], gamma, dx, ws["d16"], dgamma, None, M)       # dx0
+        self.encode_backward(dx)
+        call("mca_unpack_grads", P(self.flat_grad), P(self.garena), P(self.unpack_descs), self.n_desc, S())
+
+    def attention_bwd(self, l):
+        ws = self.ws
+        call("mca_attn_bwd", P(ws["qkv"][l]), P(ws["ao"][l]), P(ws["dattn"]), P(ws["lse"][l]), P(self.k_tiles_q),
+             self.n_kt, P(self.qt_list), P(self.k_tiles), int(self.q_tiles.shape[0]), P(self.rowbits), P(self.keygrp),
+             P(ws["padding"]), P(ws["kt_class"]), P(ws["delta"]), P(ws["ucorr"]), P(ws["dq_acc"]), P(ws["dqkv"]),
+             self.B, self.N, self.H, S())
+
+    def encode_backward(self, dx0):
+        pl, ws = self.plan, self.ws
+        if pl.F:
+            call("mca_batchsum_rows", P(dx0), P(self.gview("fusion_tokens")), pl.F, D, self.B, self.N, pl.n_tok, 1, S())
+        for i, (name, enc) in enumerate(zip(pl.names, self.model.encoder_specs)):
+            pre = f"encoders.{name}."
+            L = enc["max_tokens"]
+            rows = self.B * L
+            e = ws["enc"][name]
+            if enc["type"] == "EmbeddedSequenceEncoder":
+                kin, kp = enc["input_size"], self.enc_kpad[name]
+                pad = self._pad_mod(i)
+                ops.layernorm512_bwd(dx0, e["z"], e["st_out"], self.pview(pre + "token_encoder.2.weight"), e["dz32"],
+                                     e["dz16"], self.gview(pre + "token_encoder.2.weight"),
+                                     self.gview(pre + "token_encoder.2.bias"), rows, pad=pad, seg_len=L,
+                                     out_rows_per_b=self.N, out_row_off=pl.offsets[i])
+                call("mca_colsum", P(e["dz32"]), D, P(self.gview(pre + "token_encoder.1.bias")), D, rows, S())
+                self._dw(pre + "proj", e["dz16"], e["y"], D, kp, rows)
+                ops.gemm(e["dz16"], 0, self.W(pre + "proj"), 1, rows, kp, D, _lib.EPI_F32, e["dy"])
+                call("mca_layernorm_in_param_bwd", P(e["dy"]), kp, P(e["tokens"]), P(e["st_in"]), P(pad),
+                     P(self.gview(pre + "token_encoder.0.weight")), P(self.gview(pre + "token_encoder.0.bias")), kin,
+                     rows, S())
+            elif enc["type"] == "TabularEncoder":
+                ops.layernorm512_bwd(dx0, e["z"], e["st_out"], self.pview(pre + "value_encoder.norm.weight"), e["dz32"],
+                                     e["dz16"], self.gview(pre + "value_encoder.norm.weight"),
+                                     self.gview(pre + "value_encoder.norm.bias"), rows, pad=e["vpad"], seg_len=L,
+                                     out_rows_per_b=self.N, out_row_off=pl.offsets[i])
+                call("mca_colsum", P(e["dz32"]), D, P(self.gview(pre + "value_encoder.linear2.bias")), D, rows, S())
+                self._dw(pre + "proj", e["dz16"], e["h1"], D, D, rows)
+                ops.gemm(e["dz16"], 0, self.W(pre + "proj"), 1, rows, D, D, _lib.EPI_F32, e["dh1"])
+                call("mca_tabular_bwd", P(e["dh1"]), P(e["values"]), P(self.pview(pre + "value_encoder.linear1.weight")),
+                     P(self.pview(pre + "value_encoder.linear1.bias")),
+                     P(self.gview(pre + "value_encoder.linear1.weight")), P(self.gview(pre + "value_encoder.linear1.bias")),
+                     None, None, float(enc.get("max_value", 10000)), float(enc.get("padding_idx", -1)), D, rows, S())
+                gemb = self.gview(pre + "token_encoder.embedding.weight")
+                call("mca_batchsum_rows", P(dx0), P(gemb), L, D, self.B, self.N, pl.offsets[i], 1, S())
+                gemb[int(enc.get("padding_idx", -1)) % L].zero_()  # nn.Embedding padding_idx row gets no gradient
+
+    # ------------------------------------------------------------------------------------------ optimiser
+    def configure_optimizer(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=2.0,
+                            schedule="constant", warmup_steps=0, total_steps=1):
+        self.adamw_cfg = ops.AdamWCfg(lr, betas[0], betas[1], eps, weight_decay, max_norm,
+                                      1 if schedule == "cosine" else 0, warmup_steps, total_steps)
+
+    def optimizer_step(self):
+        """Gradient all-reduce (data parallel mean, train_accel_gpu.py:93,115) + clip + AdamW + weight re-pack."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        call("mca_clip_adamw_step", P(self.flat), P(self.flat_grad), P(self.exp_avg), P(self.exp_avg_sq), self.n_flat,
+             P(self.sumsq), P(self.step_dev), P(self.total_norm), 1.0 / self.world, ctypes.addressof(self.adamw_cfg), S())
+        self.pack_weights()
+
+    def forward_backward(self, batch):
+        """One fused training pass without autograd: forward, loss, backward.  Returns the loss summary tensor."""
+        pooled = self.trunk_forward(batch)
+        _, summary = self.loss_forward(pooled)
+        self.flat_grad.zero_()
+        dpooled = self.loss_backward(self.ws["w_default"])
+        self.trunk_backward(dpooled)
+        return summary

@@ -1,0 +1,117 @@
+"""Typed ctypes signatures for every entry point of include/mca_b200.h, plus thin tensor-taking wrappers.
+
+Pointers are taken from torch tensors (`data_ptr()`), the stream is torch's current CUDA stream; nothing here
+allocates, copies or synchronises.  Every wrapper raises on a non-zero status (AssertionError for shape errors like
+the reference, MCAKernelError otherwise).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+VP, I32, I64, F32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+PACK_DESC_DTYPE = np.dtype([
+    ("src_off", "<i8"), ("dst_off", "<i8"), ("rows", "<i4"), ("cols", "<i4"), ("dst_ld", "<i4"), ("dst_row0", "<i4"),
+    ("mode", "<i4"), ("half", "<i4"), ("scale", "<f4"), ("n_splits", "<i4"), ("split_stride", "<i8")], align=True)
+
+
+class AdamWCfg(C.Structure):
+    _fields_ = [("lr", F32), ("beta1", F32), ("beta2", F32), ("eps", F32), ("weight_decay", F32), ("max_norm", F32),
+                ("lr_mode", I32), ("warmup_steps", I64), ("total_steps", I64)]
+
+
+_SIGS = {
+    "mca_version": [],
+    "mca_gemm_effective_splits": [I32, I32],
+    "mca_gemm_bf16": [VP, I32, I64, VP, I32, I64, I32, I32, I32, I32, I32, VP, I64, VP, I64, VP, I64, VP, F32, VP],
+    "mca_build_offsets": [VP, VP, VP, I32, I32, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP],
+    "mca_layernorm512_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I64, VP],
+    "mca_layernorm512_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I64, VP],
+    "mca_layernorm_in_fwd": [VP, VP, VP, VP, VP, VP, I32, I32, I64, VP, VP],
+    "mca_layernorm_in_param_bwd": [VP, I32, VP, VP, VP, VP, VP, I32, I64, VP],
+    "mca_colsum": [VP, I32, VP, I32, I64, VP],
+    "mca_pack_weights": [VP, VP, VP, I32, VP],
+    "mca_unpack_grads": [VP, VP, VP, I32, VP],
+    "mca_broadcast_rows": [VP, VP, I32, I32, I32, I32, I32, VP],
+    "mca_batchsum_rows": [VP, VP, I32, I32, I32, I32, I32, I32, VP],
+    "mca_cast_f32_bf16": [VP, I64, VP, I64, I64, I32, VP],
+    "mca_attn_fwd": [VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
+    "mca_attn_bwd": [VP, VP, VP, VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
+    "mca_pool_attn_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
+    "mca_pool_attn_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
+    "mca_small_gemm_f32": [VP, I64, I64, VP, I64, I64, VP, I64, VP, I64, I32, I32, I32, F32, I32, VP],
+    "mca_contrastive_allpairs_fwd": [VP, VP, VP, I32, VP, I32, I32, I32, I32, I32, I32, F32, F32, VP, VP, VP, VP],
+    "mca_contrastive_allpairs_bwd": [VP, VP, VP, I32, VP, I32, I32, I32, I32, I32, I32, VP, VP, VP, VP],
+    "mca_clip_adamw_step": [VP, VP, VP, VP, I64, VP, VP, VP, F32, VP, VP],
+    "mca_tabular_fwd": [VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
+    "mca_tabular_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
+    "mca_embedding_renorm": [VP, I32, I32, F32, VP],
+    "mca_add_rows": [VP, VP, VP, I32, I32, I32, I32, I32, I32, VP],
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS.keys())
+
+_bound = {}
+
+
+def fn(name: str):
+    f = _bound.get(name)
+    if f is None:
+        f = getattr(_lib.lib(), name)
+        f.argtypes = _SIGS[name]
+        f.restype = I32
+        _bound[name] = f
+    return f
+
+
+def P(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    rc = fn(name)(*args)
+    if rc != 0:
+        _lib.check(rc, name)
+
+
+# ------------------------------------------------------------------------------------------------- wrappers
+def gemm(A, a_mn, B, b_mn, M, N, K, mode, out0, ld0=None, out1=None, ld1=0, aux0=None, ldaux=0, bias=None, alpha=1.0,
+         k_splits=1, lda=None, ldb=None):
+    """out = A·Bᵀ on tcgen05; see mca_gemm_bf16 in include/mca_b200.h."""
+    call("mca_gemm_bf16", P(A), int(a_mn), int(lda if lda is not None else A.stride(0)), P(B), int(b_mn),
+         int(ldb if ldb is not None else B.stride(0)), int(M), int(N), int(K), int(k_splits), int(mode), P(out0),
+         int(ld0 if ld0 is not None else out0.stride(-2)), P(out1), int(ld1), P(aux0), int(ldaux), P(bias),
+         float(alpha), S())
+
+
+def effective_splits(K: int, k_splits: int) -> int:
+    f = fn("mca_gemm_effective_splits")
+    return int(f(int(K), int(k_splits)))
+
+
+def layernorm512_fwd(x, gamma, beta, y32, y16, stats, rows, pad=None, pe=None, seg_len=0, out_rows_per_b=0,
+                     out_row_off=0):
+    call("mca_layernorm512_fwd", P(x), P(gamma), P(beta), P(y32), P(y16), P(stats), P(pad), P(pe), int(seg_len),
+         int(out_rows_per_b), int(out_row_off), int(rows), S())
+
+
+def layernorm512_bwd(dy, x, stats, gamma, dx32, dx16, dgamma, dbeta, rows, pad=None, seg_len=0, out_rows_per_b=0,
+                     out_row_off=0):
+    call("mca_layernorm512_bwd", P(dy), P(x), P(stats), P(gamma), P(dx32), P(dx16), P(dgamma), P(dbeta), P(pad),
+         int(seg_len), int(out_rows_per_b), int(out_row_off), int(rows), S())
+
+
+def small_gemm(A, sam, sak, Bm, sbn, sbk, Cm, ldc, M, N, K, alpha=1.0, accumulate=False, add=None, ldadd=0):
+    call("mca_small_gemm_f32", P(A), int(sam), int(sak), P(Bm), int(sbn), int(sbk), P(Cm), int(ldc), P(add), int(ldadd),
+         int(M), int(N), int(K), float(alpha), int(bool(accumulate)), S())

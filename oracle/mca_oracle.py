@@ -135,7 +135,12 @@ def tabular_encode(sd: dict, prefix: str, data: dict, max_value: float, padding_
         scale = torch.where(norms > 1.0, 1.0 / (norms + 1e-7), torch.ones_like(norms))
         if renorm_in_place:
             emb.mul_(scale)  # nn.Embedding(max_norm=...) mutates the weight
-    x_t = emb  # index = arange(n): every row, in order
+    # index = arange(n): every row, in order; the padding_idx row (-1 -> n-1) receives no gradient
+    n_rows = emb.shape[0]
+    pi = int(padding_value) % n_rows
+    keep = torch.ones(n_rows, 1, dtype=emb.dtype)
+    keep[pi] = 0.0
+    x_t = emb * keep + (emb * (1.0 - keep)).detach()
     v = values.unsqueeze(-1)
     pad = v == padding_value
     v = torch.clamp(v, max=max_value)
