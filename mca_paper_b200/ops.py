@@ -51,7 +51,6 @@ _SIGS = {
     "mca_tabular_fwd": [VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_tabular_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_embedding_renorm": [VP, I32, I32, F32, VP],
-    "mca_add_rows": [VP, VP, VP, I32, I32, I32, I32, I32, I32, VP],
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS.keys())
@@ -79,8 +78,23 @@ def S():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name: str, *args):
-    rc = fn(name)(*args)
+# kernels launched by each entry point (memsets not counted) — bench.py reports the per-step total
+KERNELS_PER_CALL = {"mca_build_offsets": 2, "mca_attn_fwd": 2, "mca_attn_bwd": 3, "mca_pool_attn_bwd": 3,
+                    "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3}
+COUNT = {"n": 0}
+PROFILE = {"on": False, "events": []}
+
+
+def call(name: str, *args, tag: str = ""):
+    COUNT["n"] += KERNELS_PER_CALL.get(name, 1)
+    if PROFILE["on"]:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(name)(*args)
+        b.record()
+        PROFILE["events"].append((name, tag, a, b))
+    else:
+        rc = fn(name)(*args)
     if rc != 0:
         _lib.check(rc, name)
 
@@ -92,7 +106,7 @@ def gemm(A, a_mn, B, b_mn, M, N, K, mode, out0, ld0=None, out1=None, ld1=0, aux0
     call("mca_gemm_bf16", P(A), int(a_mn), int(lda if lda is not None else A.stride(0)), P(B), int(b_mn),
          int(ldb if ldb is not None else B.stride(0)), int(M), int(N), int(K), int(k_splits), int(mode), P(out0),
          int(ld0 if ld0 is not None else out0.stride(-2)), P(out1), int(ld1), P(aux0), int(ldaux), P(bias),
-         float(alpha), S())
+         float(alpha), S(), tag=f"{'MN' if a_mn else 'K'}{'MN' if b_mn else 'K'}_m{M}_n{N}_k{K}_e{mode}")
 
 
 def effective_splits(K: int, k_splits: int) -> int:

@@ -1,0 +1,137 @@
+"""Fused training step: H2D of the batch -> forward -> all-pairs loss -> backward -> (DP all-reduce) -> clip + AdamW
+-> weight re-pack, replayed from CUDA graphs (shapes are static: Q6, the batch size is baked into the model).
+
+Replaces the reference hot loop train_accel_gpu.py:110-119 (move_to, model(batch), zero_grad, backward,
+clip_grad_norm_, optimizer.step, lr_scheduler.step) without its per-step host synchronisations
+(train_accel_gpu.py:126-130 log every scalar with .to("cpu"); here the loss stays on the device until asked for).
+
+Data parallelism: one process per GPU, identical replicas, B samples per rank; three collectives per
+step over NCCL/NVLink — all-gather of the pooled block [B,R,512], reduce-scatter of its gradient, all-reduce of the
+flat gradient buffer — issued between graph segments.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .engine import Engine
+
+
+class Trainer:
+    def __init__(self, model, lr: float = 1e-4, clip: float = 2.0, weight_decay: float = 0.01, betas=(0.9, 0.999),
+                 eps: float = 1e-8, schedule: str = "constant", warmup_steps: int = 0, total_steps: int = 1,
+                 use_graphs: bool = True, process_group=None):
+        self.model = model
+        self.eng: Engine = model.engine
+        self.eng.ensure_flat()
+        self.eng.configure_optimizer(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=clip,
+                                     schedule=schedule, warmup_steps=warmup_steps, total_steps=total_steps)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.eng.set_distributed(torch.distributed.get_world_size(process_group),
+                                     torch.distributed.get_rank(process_group), process_group)
+        self.use_graphs = use_graphs
+        self._graphs = None
+        self._dev_batch: Optional[Dict[str, Dict[str, torch.Tensor]]] = None
+        self._pinned: Optional[Dict[str, Dict[str, torch.Tensor]]] = None
+        self.eng.pack_weights()
+        self.h2d_bytes = 0
+        self.kernel_launches_per_step = None
+
+    # ------------------------------------------------------------------------------------------ staging
+    def _ensure_staging(self, host_batch):
+        if self._dev_batch is not None:
+            return
+        dev = self.eng.device
+        self._dev_batch, self._pinned = {}, {}
+        n = 0
+        for m, d in host_batch.items():
+            self._dev_batch[m], self._pinned[m] = {}, {}
+            for k, v in d.items():
+                self._dev_batch[m][k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                self._pinned[m][k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                n += v.numel() * v.element_size()
+        self.h2d_bytes = n
+
+    def stage(self, host_batch):
+        """Copy a host batch into the pinned staging area and enqueue its H2D copy on the current stream."""
+        self._ensure_staging(host_batch)
+        for m, d in host_batch.items():
+            for k, v in d.items():
+                self._pinned[m][k].copy_(v)
+                self._dev_batch[m][k].copy_(self._pinned[m][k], non_blocking=True)
+
+    def h2d(self):
+        """Enqueue only the H2D copies from the (already filled) pinned buffers."""
+        for m, d in self._pinned.items():
+            for k, v in d.items():
+                self._dev_batch[m][k].copy_(v, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------ step pieces
+    def _seg_forward(self):
+        self._pooled = self.eng.trunk_forward(self._dev_batch)
+
+    def _seg_loss(self):
+        eng = self.eng
+        eng.loss_forward(self._pooled)
+        eng.flat_grad.zero_()
+        self._dpooled = eng.loss_backward(eng.ws["w_default"])
+
+    def _seg_backward(self):
+        self.eng.trunk_backward(self._dpooled)
+
+    def _seg_optim(self):
+        self.eng.optimizer_step()
+
+    def _run_eager(self):
+        self._seg_forward()
+        self._seg_loss()
+        self._seg_backward()
+        self._seg_optim()
+
+    def _capture(self):
+        eng = self.eng
+        # warm-up on a side stream (allocations, attribute setting, NCCL init) before capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._run_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if eng.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_eager()
+            self._graphs = [("graph", g)]
+        else:
+            # collectives stay outside the graphs: [fwd] all_gather+loss(eager: contains 2 collectives) [bwd] all_reduce+optim
+            g1, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._seg_forward()
+            self._seg_loss()
+            with torch.cuda.graph(g3, pool=g1.pool()):
+                self._seg_backward()
+            self._seg_optim()
+            self._graphs = [("graph", g1), ("eager", self._seg_loss), ("graph", g3), ("eager", self._seg_optim)]
+        torch.cuda.synchronize()
+
+    def step_staged(self):
+        """Run one optimisation step on the batch currently in the device staging buffers; returns the device
+        tensor [loss, fcl_loss, no-fcl_loss, #valid losses] (no synchronisation)."""
+        if not self.use_graphs:
+            self._run_eager()
+        else:
+            if self._graphs is None:
+                self._capture()
+            for kind, g in self._graphs:
+                if kind == "graph":
+                    g.replay()
+                else:
+                    g()
+        return self.eng.ws["summary"]
+
+    def step(self, host_batch):
+        """End-to-end step from a HOST batch (dict of dict of CPU tensors): pinned staging, H2D, fused step."""
+        self.stage(host_batch)
+        return self.step_staged()

@@ -15,10 +15,13 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
 
 
-def run(cfg, variant, tag, check_bwd=True):
+def run(cfg, variant, tag, check_bwd=True, conditioned=False):
     kw = C.get_model_config(cfg)
     torch.manual_seed(0)
     model = MCA(**kw)
+    if conditioned:  # small pooled embeddings and T = 1: forward rounding is no longer amplified by a sharp softmax
+        with torch.no_grad():
+            model.attn_pool.to_out.weight.mul_(0.05); model.return_tokens.mul_(0.02); model.loss.loss_fn.logit_scale.fill_(0.0)
     sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model = model.to(dev)
     batch = S.make_batch(cfg, seed=1, variant=variant)
@@ -44,9 +47,12 @@ def run(cfg, variant, tag, check_bwd=True):
     print("  padding bit-exact  ", bool((eng.ws["padding"].cpu().bool() == padding_ref).all()))
     print("  final tokens (bf16 copy of LN) rel", rel(eng.ws["xf_16"], xf_ref.reshape(eng.M, 512)))
     print("  pooled             rel", rel(eng.ws["pooled"], pooled_ref))
+    worst_emb = 0
     for k in ref:
         if k in ("losses", "modality_sample_mask"): continue
-        print(f"  out[{k}] rel", rel(out[k], ref[k]))
+        if isinstance(k, str) and "loss" in k: print(f"  out[{k}] rel", rel(out[k], ref[k]))
+        else: worst_emb = max(worst_emb, rel(out[k], ref[k]))
+    print("  worst embedding rel", worst_emb)
     worst = 0
     for k, v in ref["losses"].items():
         a = out["losses"][k]
@@ -78,6 +84,10 @@ def run(cfg, variant, tag, check_bwd=True):
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "cmu"):
     run(C.tiny_config("cmu", fcl=True), "full", "tiny CMU MCA-fcl, full length")
+if which in ("all", "cond"):
+    run(C.tiny_config("cmu", fcl=True), "full", "tiny CMU MCA-fcl, full length, well-conditioned loss", conditioned=True)
+    run(C.tiny_config("cmu", fcl=True), "dropout_ragged", "tiny CMU MCA-fcl, ragged, well-conditioned loss", conditioned=True)
+    run(C.tiny_config("tcga", fcl=True, bimodal=True, non_fusion_fcl=True), "tcga", "tiny TCGA, well-conditioned", conditioned=True)
 if which in ("all", "ragged"):
     run(C.tiny_config("cmu", fcl=True), "dropout_ragged", "tiny CMU MCA-fcl, absent + ragged")
 if which in ("all", "mma"):
