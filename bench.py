@@ -268,6 +268,10 @@ def main():
             agg[k] = (tot + ms, n + 1)
         per_kernel = {k: {"ms_total_per_step": v[0] / 2, "launches_per_step": v[1] // 2, "us_avg": v[0] / v[1] * 1e3}
                       for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        if os.environ.get("MCA_BENCH_TABLE"):
+            os.makedirs(os.path.dirname(os.environ["MCA_BENCH_TABLE"]) or ".", exist_ok=True)
+            with open(os.environ["MCA_BENCH_TABLE"], "w") as f:
+                json.dump(per_kernel, f, indent=1)
         peaks = read_peaks()
         fl = algorithmic_flops(eng.plan, B, eng.H, eng.depth, eng.I)
         top = next(iter(per_kernel))

@@ -115,6 +115,16 @@ int mca_layernorm_in_param_bwd(const float* dy, int ld_dy, const float* x, const
                                float* dw, float* db, int width, long long rows, void* stream);
 int mca_colsum(const float* a, int ld, float* out, int width, long long rows, void* stream);
 
+/* TabularEncoder pieces (encoders.py:25-37,55-72,90-96): in-place max_norm renormalisation of the embedding table
+ * (nn.Embedding(max_norm=1.0) semantics), h1 = relu(w1*min(v,max_value)+b1) as the bf16 operand of the d x d Linear
+ * (vpad[r] = v[r]==padding_value), and the parameter gradients of that first Linear. */
+int mca_embedding_renorm(float* emb, int rows, int d, float max_norm, void* stream);
+int mca_tabular_fwd(const float* values, const float* w1, const float* b1, void* h1_bf16, uint8_t* vpad,
+                    float max_value, float padding_value, int d, long long rows, void* stream);
+int mca_tabular_bwd(const float* dh1, const float* values, const float* w1, const float* b1, float* dw1, float* db1,
+                    const void* unused0, const void* unused1, float max_value, float padding_value, int d,
+                    long long rows, void* stream);
+
 /* fp32 state_dict-layout weights -> bf16 kernel-layout operands, and the inverse for gradients. */
 int mca_pack_weights(const float* params, void* arena_bf16, const mca_pack_desc* descs_dev, int n_desc, void* stream);
 int mca_unpack_grads(float* grads, const float* partials, const mca_pack_desc* descs_dev, int n_desc, void* stream);

@@ -1,0 +1,189 @@
+"""GPU (-m gpu): the whole fused path (model.MCA through the C ABI) against the golden vectors frozen from the live
+reference, against the CPU oracle, and through size-independent properties at BASELINE.json's full size.
+
+Tolerances (north_star): mask/offset/index outputs bit-exact; bf16 compute path: embeddings and loss within 2e-2
+relative of the fp32 reference."""
+import math
+
+import pytest
+import torch
+
+from mca_paper_b200 import config as C, synthetic as S
+from mca_paper_b200.model import MCA
+from mca_paper_b200.trainer import Trainer
+from oracle import mca_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+BF16_TOL = 2e-2
+
+
+@pytest.mark.parametrize("case", list(H.CASES))
+def test_model_matches_reference_golden(case):
+    gold = H.load_golden(case)
+    cfg, kw, model, sd, batch = H.build_case(case)
+    assert H.weights_checksum(sd) == gold["weights_sha256"] and H.batch_checksum(batch) == gold["batch_sha256"]
+    model = model.to(dev)
+    out = model(S.batch_to(batch, dev))
+    assert [H.key_to_str(k) for k in out.keys()] == gold["output_keys"]                 # Q17 key order
+    assert list(out["losses"].keys()) == list(gold["losses"].keys())
+    for k, v in out.items():
+        if k in ("losses", "modality_sample_mask") or (isinstance(k, str) and "loss" in k):
+            continue
+        assert v.shape == (model.batch_size, 512)
+        assert H.rel_err(v, gold["embeddings"][H.key_to_str(k)]) < BF16_TOL, k
+    assert abs(out["loss"].item() - gold["loss"].item()) < BF16_TOL * abs(gold["loss"].item())
+    for k, v in gold["losses"].items():
+        if torch.isnan(v):
+            assert torch.isnan(out["losses"][k]), k                                      # empty-mask pairs stay NaN
+    if gold["fcl_loss"] is not None:
+        assert abs(out["fcl_loss"].item() - gold["fcl_loss"].item()) < BF16_TOL * abs(gold["fcl_loss"].item())
+        assert abs(out["no-fcl_loss"].item() - gold["no-fcl_loss"].item()) < BF16_TOL * abs(gold["no-fcl_loss"].item())
+    for k, v in gold["modality_sample_mask"].items():
+        assert torch.equal(out["modality_sample_mask"][k].cpu(), v)                      # bit-exact
+    out["loss"].backward()
+    # gradient norms: the logits are un-normalised and sharp at random init, so forward rounding is amplified in
+    # d(loss)/d(logits); the well-conditioned gradient test below is the tight one
+    bad = []
+    for k, p in model.named_parameters():
+        n = gold["grad_norms"][k]
+        if n == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        elif abs(p.grad.norm().item() - n) > 0.15 * n:
+            bad.append((k, p.grad.norm().item(), n))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("kind,kwargs,variant", [
+    ("cmu", dict(fcl=True), "dropout_ragged"),
+    ("tcga", dict(fcl=True, bimodal=True, non_fusion_fcl=True), "tcga"),
+    ("cmu", dict(zorro=True, fcl=False), "dropout_full"),
+])
+def test_gradients_match_oracle_well_conditioned(kind, kwargs, variant):
+    """Every parameter gradient against oracle autograd, with small pooled embeddings and T = 1 so that bf16 forward
+    rounding is not amplified by a saturated softmax (tolerance 5e-2 relative L2 per tensor, median below 1.5e-2)."""
+    cfg = C.tiny_config(kind, **kwargs)
+    kw = C.get_model_config(cfg)
+    torch.manual_seed(0)
+    model = MCA(**kw)
+    with torch.no_grad():
+        model.attn_pool.to_out.weight.mul_(0.05)
+        model.return_tokens.mul_(0.02)
+        model.loss.loss_fn.logit_scale.fill_(0.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = S.make_batch(cfg, seed=1, variant=variant)
+    names = [k for k, _ in model.named_parameters()]
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    sd2 = dict(sd)
+    sd2.update(params)
+    ref = O.mca_forward(sd2, kw, batch)
+    ref["loss"].backward()
+    model = model.to(dev)
+    out = model(S.batch_to(batch, dev))
+    out["loss"].backward()
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-3 * abs(ref["loss"].item())
+    errs = []
+    for k, p in model.named_parameters():
+        g = params[k].grad
+        if g is None or float(g.abs().max()) == 0.0:
+            continue
+        errs.append((H.rel_err(p.grad, g), k))
+    errs.sort(reverse=True)
+    assert errs[0][0] < 5e-2, errs[:5]
+    assert errs[len(errs) // 2][0] < 1.5e-2, errs[len(errs) // 2]
+
+
+def test_no_loss_and_eval_mode_outputs():
+    cfg, kw, model, sd, batch = H.build_case("tiny_cmu_mma_absent")
+    model = model.to(dev).eval()
+    with torch.no_grad():
+        out = model(S.batch_to(batch, dev), no_loss=True)
+    assert list(out.keys()) == model.modality_types + ["fusion", "modality_sample_mask"]   # model.py:193-194,477
+    ref = O.mca_forward(sd, kw, batch, no_loss=True)
+    for k in model.modality_types + ["fusion"]:
+        assert H.rel_err(out[k], ref[k]) < BF16_TOL
+
+
+def test_nonfinite_tokens_raise():
+    cfg, kw, model, sd, batch = H.build_case("tiny_cmu_fcl_full")
+    model = model.to(dev)
+    batch["COVAREP"]["tokens"][0, 0, 0] = float("nan")
+    with pytest.raises(Exception):                         # encoders.py:197-198
+        model(S.batch_to(batch, dev))
+
+
+def test_wrong_batch_size_asserts():
+    cfg, kw, model, sd, batch = H.build_case("tiny_cmu_fcl_full")
+    model = model.to(dev)
+    small = {m: {k: v[:4] for k, v in d.items()} for m, d in batch.items()}
+    with pytest.raises(AssertionError):                    # Q6: batch must equal config.batch_size (model.py:454)
+        model(S.batch_to(small, dev))
+
+
+def test_full_size_cmu_config1_forward_against_oracle():
+    """BASELINE.json config 2 at full size (N = 2538, 14 losses): loss and every embedding vs the CPU oracle."""
+    cfg = C.named_config("CMU_config1")
+    kw = C.get_model_config(cfg)
+    torch.manual_seed(43)
+    model = MCA(**kw)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = S.make_batch(cfg, seed=1, variant="full")
+    with torch.no_grad():
+        ref = O.mca_forward(sd, kw, batch)
+    model = model.to(dev)
+    with torch.no_grad():
+        out = model(S.batch_to(batch, dev))
+    assert abs(out["loss"].item() - ref["loss"].item()) < BF16_TOL * abs(ref["loss"].item())
+    for k, v in ref.items():
+        if k in ("losses", "modality_sample_mask") or (isinstance(k, str) and "loss" in k):
+            continue
+        assert H.rel_err(out[k], v) < BF16_TOL, k
+
+
+def test_full_size_properties_d40_dropout():
+    """Size-independent properties at full size with modality dropout (config 3): deterministic forward, padded
+    positions never influence live outputs, absent-modality loss rows are excluded (NaN pairs when nothing is left)."""
+    cfg = C.named_config("CMU_config1_d40")
+    kw = C.get_model_config(cfg)
+    torch.manual_seed(43)
+    model = MCA(**kw).to(dev).eval()
+    batch = S.make_batch(cfg, seed=4, variant="dropout_ragged")
+    with torch.no_grad():
+        a = model(S.batch_to(batch, dev))
+        b = model(S.batch_to(batch, dev))
+    for k in model.modality_types + ["fusion"]:
+        assert torch.equal(a[k], b[k])                     # forward is bit-deterministic
+    # garbage in padded token slots must not change anything (they are zeroed / never read as keys)
+    noisy = {m: {k: v.clone() for k, v in d.items()} for m, d in batch.items()}
+    for m in noisy:
+        pad = noisy[m]["attention_mask"]
+        noisy[m]["tokens"][pad] = 123.0
+    with torch.no_grad():
+        c = model(S.batch_to(noisy, dev))
+    for k in model.modality_types + ["fusion"]:
+        assert torch.equal(a[k], c[k])
+    assert torch.isfinite(a["loss"])
+
+
+def test_training_step_reduces_loss_and_matches_autograd_path():
+    cfg = C.tiny_config("cmu", fcl=True)
+    kw = C.get_model_config(cfg)
+    torch.manual_seed(0)
+    model = MCA(**kw).to(dev)
+    batch = S.make_batch(cfg, seed=1, variant="dropout_ragged")
+    # autograd path gradient == fused trainer path gradient (same kernels, two drivers)
+    out = model(S.batch_to(batch, dev))
+    out["loss"].backward()
+    g_auto = torch.cat([p.grad.flatten() for p in model.parameters()])
+    tr = Trainer(model, lr=1e-4, clip=2.0, use_graphs=True)
+    tr.stage(batch)
+    tr.eng.pack_weights()
+    tr._seg_forward(), tr._seg_loss(), tr._seg_backward()
+    g_fused = torch.cat([tr.eng.gview(k).flatten() for k, _ in model.named_parameters()])
+    assert H.rel_err(g_fused, g_auto) < 1e-3
+    losses = []
+    for _ in range(12):
+        s = tr.step(batch)
+        losses.append(float(s[0]))
+    assert all(math.isfinite(x) for x in losses) and losses[-1] < losses[0]

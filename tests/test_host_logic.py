@@ -1,0 +1,150 @@
+"""CPU: host-side logic of the product — static plan (bit-exact vs oracle and vs reference hashes), tile schedule
+properties, config loader, state_dict schema, synthetic batches, C-ABI symbol export, loud failure without CUDA."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mca_paper_b200 import _lib, config as C, ops, synthetic as S
+from mca_paper_b200.model import MCA
+from mca_paper_b200.plan import StaticPlan
+from oracle import mca_oracle as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_plan(kw):
+    return StaticPlan(kw["encoder_configs"], kw["num_fusion_tokens"], kw["fusion_combos"], kw["fcl"], kw["zorro"],
+                      kw["no_fusion"], kw["bimodal_contrastive"], kw["non_fusion_fcl"])
+
+
+@pytest.mark.parametrize("name", ["CMU_config1", "CMU_config1_z", "CMU_config1_d40", "TCGA_config1"])
+def test_plan_masks_bit_exact(name):
+    kw = C.get_model_config(C.named_config(name))
+    p, t = make_plan(kw), O.static_tables(kw)
+    assert np.array_equal(p.token_types, t["token_types"].numpy())
+    assert np.array_equal(p.attn_mask, t["attn_mask"].numpy())
+    assert np.array_equal(p.pool_mask, t["pool_mask"].numpy())
+    assert p.return_token_types == t["return_token_types"] and p.combos == t["combos"]
+    plan, _ = O.loss_plan(kw, t)
+    assert [x["name"] for x in plan] == p.loss_names
+    for x, y in zip(plan, p.loss_plan):
+        assert (x["a"], x["b"]) == (y["a"], y["b"])
+        assert sum(1 << i for i in x["all"]) == y["all"] and sum(1 << i for i in x["any"]) == y["any"]
+        assert bool(x["fcl"]) == bool(y["fcl"])
+
+
+def test_plan_matches_reference_hashes():
+    static = torch.load(H.GOLDEN_DIR + "/static_tables.pt", weights_only=False)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for name, g in static.items():
+        p = make_plan(C.get_model_config(C.named_config(name)))
+        assert sha(p.attn_mask) == g["attn_mask_sha256"] and sha(p.pool_mask) == g["pool_mask_sha256"]
+        assert sha(p.token_types) == g["token_types_sha256"]
+        assert p.allowed_pairs == g["attn_allowed_pairs"] and p.loss_names == g["loss_names"]
+
+
+@pytest.mark.parametrize("name", ["CMU_config1", "CMU_config1_z", "TCGA_config1"])
+def test_tile_schedule_covers_exactly_the_allowed_pairs(name):
+    p = make_plan(C.get_model_config(C.named_config(name)))
+    allowed = ~p.attn_mask
+    covered = np.zeros_like(allowed)
+    for qs, ql, off, cnt in p.q_tiles:
+        for ki, flag in p.kt_list[off:off + cnt]:
+            ks, kl = p.tiles[ki]
+            blk = allowed[qs:qs + ql, ks:ks + kl]
+            assert blk.any()
+            assert (flag == 0) == bool(blk.all())
+            assert not covered[qs:qs + ql, ks:ks + kl].any()
+            covered[qs:qs + ql, ks:ks + kl] = True
+    assert not (allowed & ~covered).any()          # nothing allowed is skipped
+    # tiles partition [0, N) and never straddle a modality boundary
+    assert p.tiles[0, 0] == 0 and (p.tiles[:, 0] + p.tiles[:, 1])[-1] == p.N
+    assert np.array_equal(p.tiles[1:, 0], (p.tiles[:, 0] + p.tiles[:, 1])[:-1]) and p.tiles[:, 1].max() <= 128
+    for s, l in p.tiles:
+        assert len(set(p.keygrp[s:s + l].tolist()) - set(range(p.n_mod))) <= max(0, p.n_groups - p.n_mod)
+    # transposed (backward) schedule lists the same pairs
+    fwd = {(qi, int(ki)) for qi, (_, _, off, cnt) in enumerate(p.q_tiles) for ki, _ in p.kt_list[off:off + cnt]}
+    bwd = {(int(qi), ki) for ki, (_, _, off, cnt) in enumerate(p.k_tiles_q) for qi, _ in p.qt_list[off:off + cnt]}
+    assert fwd == bwd
+
+
+def test_group_bitmasks_reconstruct_masks():
+    p = make_plan(C.get_model_config(C.named_config("CMU_config1")))
+    rec = ~(((p.rowbits[:, None] >> p.keygrp[None, :].astype(np.uint32)) & 1).astype(bool))
+    assert np.array_equal(rec, p.attn_mask)
+
+
+@pytest.mark.parametrize("name", ["CMU_config1", "CMU_config1_z", "TCGA_config1"])
+def test_state_dict_schema_matches_reference(name):
+    static = torch.load(H.GOLDEN_DIR + "/static_tables.pt", weights_only=False)[name]
+    model = MCA(**C.get_model_config(C.named_config(name)))
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == static["state_dict_schema"]
+    assert [k for k, _ in model.named_parameters()] == static["param_names"]
+    assert sum(p.numel() for p in model.parameters()) == static["n_params"]
+
+
+def test_config_defaults_and_model_kwargs():
+    cfg = C.training_config({"layers": 5})
+    assert cfg.hidden_size == 512 and cfg.heads == 8 and cfg.dim_head == 64 and cfg.ff_mult == 4   # utils/config.py:40-44
+    kw = C.get_model_config(C.named_config("CMU_config1"))
+    assert set(kw) == {"dim", "depth", "heads", "dim_head", "ff_mult", "num_fusion_tokens", "encoder_configs", "batch_size",
+                       "fcl", "fcl_root", "bimodal_contrastive", "non_fusion_fcl", "fusion_combos", "zorro", "eao",
+                       "no_fusion", "mean_pool"}
+    MCA(**kw)  # swallows `eao`
+
+
+def test_bad_fusion_token_count_asserts():
+    kw = C.get_model_config(C.named_config("CMU_config1"))
+    kw["num_fusion_tokens"] = 90   # not divisible by 11 combos (model.py:416-417)
+    with pytest.raises(AssertionError):
+        MCA(**kw)
+
+
+def test_synthetic_batches():
+    cfg = C.named_config("CMU_config1_d40")
+    b = S.make_batch(cfg, seed=3, variant="dropout_ragged")
+    for name, enc in cfg["encoder_configs"].items():
+        t, m = b[name]["tokens"], b[name]["attention_mask"]
+        assert t.shape == (8, enc["max_tokens"], enc["input_size"]) and m.dtype == torch.bool
+        assert (t[m] == 0).all()
+        # suffix padding only (encoders.py:339-341)
+        assert (m[:, 1:].int() - m[:, :-1].int() >= 0).all()
+    tb = S.make_batch(C.named_config("TCGA_config1"), seed=1, variant="tcga")
+    assert tb["protein"]["attention_mask"].dtype == torch.long
+    assert torch.equal(tb["protein"]["attention_mask"].bool(), tb["protein"]["values"] == -10000)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mca_b200.h")).read()
+    declared = set(re.findall(r"^int (mca_\w+)\(", header, flags=re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(ops.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.mca_version() >= 100
+
+
+def test_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    cfg = C.tiny_config("cmu")
+    model = MCA(**C.get_model_config(cfg))
+    with pytest.raises(_lib.MCAKernelError):
+        model(S.make_batch(cfg))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mca_paper_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
