@@ -1,5 +1,6 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (fp32
-// accumulators in TMEM, double buffered) -> fused epilogues read back with tcgen05.ld.
+// accumulators in TMEM, double buffered) -> fused epilogues read back with tcgen05.ld, staged in swizzled shared
+// memory and written (and, for the in-place epilogues, pre-loaded) by TMA so every global access is a full line.
 //
 //   out[M,N] = A[M,K] * B[N,K]^T           (both operands may independently be K-major or MN-major in memory)
 //
@@ -7,6 +8,10 @@
 // to_q/to_kv/to_out, model.py:49-51 GEGLU feed-forward, encoders.py:190 token projection, and their autograd
 // transposes):  forward uses (A K-major, B K-major), dX uses (A K-major, B MN-major = the weight as stored),
 // dW uses (A MN-major, B MN-major) with split-K over the token dimension.
+//
+// Warp roles (384 threads, one CTA per SM): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-11 epilogue.  Epilogue warp w owns TMEM lane quarter w%4 (32 accumulator rows) and column half (w-4)/4
+// (64 of the tile's 128 columns); it has a private 8 KB staging area, so the epilogue needs no block-wide barrier.
 #include "mca_b200.h"
 #include "ptx.cuh"
 #include "runtime.h"
@@ -14,84 +19,58 @@
 namespace mca {
 
 constexpr int BM = 128;
+constexpr int BN = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int STAGES = 5;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_BYTES_PER_WARP = 8192;
+constexpr int GEMM_SMEM = STAGES * (A_BYTES + B_BYTES) + EPI_WARPS * EPI_BYTES_PER_WARP + 1024 /*align slack*/ + 256;
+constexpr int TMEM_COLS = 2 * BN;
 
 struct GemmParams {
   int M, N, K;
   int k_splits;
   int mode;
-  void* out0;
-  long long ld0;
-  void* out1;
-  long long ld1;
-  const void* aux0;
-  long long ldaux;
   const float* bias;
   float alpha;
 };
 
-template <int BN>
-struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = 2 * BN;
-};
+// ---- staging helpers: thread = one row of a [32 rows x 128 B] (or [32 x 64 B]) swizzled box
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+__device__ __forceinline__ uint32_t sw64_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
-// ---- epilogue: one thread = one output row, processes 32 consecutive columns held in r[]
-__device__ __forceinline__ void store_bf16_32(__nv_bfloat16* dst, const float (&v)[32]) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 q;
-    q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-    q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-    d4[i] = q;
-  }
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  return q;
 }
-__device__ __forceinline__ void store_f32_32(float* dst, const float (&v)[32]) {
-  float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-__device__ __forceinline__ void load_f32_32(const float* src, float (&v)[32]) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 q = s4[i];
-    v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
-  }
-}
-__device__ __forceinline__ void load_bf16_32(const __nv_bfloat16* src, float (&v)[32]) {
-  const uint4* s4 = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 q = s4[i];
-    v[8 * i + 0] = bf16_lo(q.x), v[8 * i + 1] = bf16_hi(q.x);
-    v[8 * i + 2] = bf16_lo(q.y), v[8 * i + 3] = bf16_hi(q.y);
-    v[8 * i + 4] = bf16_lo(q.z), v[8 * i + 5] = bf16_hi(q.z);
-    v[8 * i + 6] = bf16_lo(q.w), v[8 * i + 7] = bf16_hi(q.w);
-  }
+__device__ __forceinline__ void unpack8(const uint4 q, float* v) {
+  v[0] = bf16_lo(q.x), v[1] = bf16_hi(q.x), v[2] = bf16_lo(q.y), v[3] = bf16_hi(q.y);
+  v[4] = bf16_lo(q.z), v[5] = bf16_hi(q.z), v[6] = bf16_lo(q.w), v[7] = bf16_hi(q.w);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+               const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = base;
-  uint8_t* sB = base + STAGES * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint8_t* sB = base + STAGES * A_BYTES;
+  uint8_t* sEpi = sB + STAGES * B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + EPI_WARPS * EPI_BYTES_PER_WARP);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;  // [EPI_WARPS]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,6 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO0);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -112,11 +92,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
     }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+  if (warp == 2) tmem_alloc(tmem_holder, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -136,9 +117,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-          uint8_t* a_dst = sA + s * Cfg::A_BYTES;
-          uint8_t* b_dst = sB + s * Cfg::B_BYTES;
+          mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          uint8_t* a_dst = sA + s * A_BYTES;
+          uint8_t* b_dst = sB + s * B_BYTES;
           if constexpr (!A_MN) {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
           } else {
@@ -171,8 +152,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+          const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // K-major: 16 bf16 = 32 B along the swizzled row; rows of 8 are 1024 B apart (SBO).
@@ -191,122 +172,188 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps: TMEM -> registers -> global =====================
-    const int ew = warp & 3;  // TMEM sub-partition this warp may read
+    // ===================== epilogue warps: TMEM -> registers -> swizzled smem -> TMA store =====================
+    const int ew = warp - 4;
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    const int hf = ew >> 2;   // column half of the tile
+    uint8_t* stg = sEpi + ew * EPI_BYTES_PER_WARP;
+    uint64_t* xbar = &aux_bar[ew];
+    const bool has_aux = p.mode == MCA_EPI_RESID || p.mode == MCA_EPI_GEGLU_BWD;
     int as = 0;
-    uint32_t aph = 0;
+    uint32_t aph = 0, xph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % tiles_n;
       const int mt = (tile / tiles_n) % tiles_m;
       const int z = tile / (tiles_n * tiles_m);
       const int n0 = nt * BN;
-      const long long row = static_cast<long long>(mt) * BM + ew * 32 + lane;
-      const bool row_ok = row < p.M;
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-
-      if (p.mode == MCA_EPI_GEGLU) {
-        // columns of each 128-wide block are [64 value | 64 gate] (W1 rows interleaved on the host side)
-#pragma unroll 1
-        for (int blk = 0; blk < BN / 128; ++blk) {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t rv[32], rg[32];
-            tmem_ld32(t_row + blk * 128 + c * 32, rv);
-            tmem_ld32(t_row + blk * 128 + 64 + c * 32, rg);
-            tmem_ld_wait();
-            const int ncol = n0 + blk * 128 + c * 32;  // column of the value chunk in u
-            if (row_ok && ncol < p.N) {
-              float xv[32], gv[32], hv[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                // round to bf16 first so forward h and the backward recompute see identical u
-                xv[i] = __bfloat162float(__float2bfloat16(__uint_as_float(rv[i])));
-                gv[i] = __bfloat162float(__float2bfloat16(__uint_as_float(rg[i])));
-                hv[i] = gelu_exact(gv[i]) * xv[i];
-              }
-              __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.out1) + row * p.ld1;
-              store_bf16_32(u + ncol, xv);
-              store_bf16_32(u + ncol + 64, gv);
-              __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * p.ld0;
-              store_bf16_32(h + (ncol / 128) * 64 + c * 32, hv);
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c * 32, r);
-          tmem_ld_wait();
-          const int ncol = n0 + c * 32;
-          if (!row_ok || ncol >= p.N) continue;
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + ncol + i);
-          }
-          if (p.mode == MCA_EPI_BF16) {
-            store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out0) + row * p.ld0 + ncol, v);
-          } else if (p.mode == MCA_EPI_F32) {
-            float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(z) * p.M * p.ld0;
-            store_f32_32(o + row * p.ld0 + ncol, v);
-          } else if (p.mode == MCA_EPI_RESID) {
-            float a[32];
-            load_f32_32(reinterpret_cast<const float*>(p.aux0) + row * p.ldaux + ncol, a);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += a[i];
-            store_f32_32(reinterpret_cast<float*>(p.out0) + row * p.ld0 + ncol, v);
-            if (p.out1 != nullptr) store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out1) + row * p.ld1 + ncol, v);
-          } else if (p.mode == MCA_EPI_GEGLU_BWD) {
-            // v = dL/dh for h columns [ncol, ncol+32); u holds (value, gate) in the interleaved layout
-            const int blk = ncol / 64, off = ncol % 64;
-            const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.aux0) + row * p.ldaux + blk * 128 + off;
-            float xv[32], gv[32];
-            load_bf16_32(u, xv);
-            load_bf16_32(u + 64, gv);
-            float dxv[32], dgv[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              dxv[i] = v[i] * gelu_exact(gv[i]);
-              dgv[i] = v[i] * xv[i] * gelu_exact_grad(gv[i]);
-            }
-            __nv_bfloat16* du = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * p.ld0 + blk * 128 + off;
-            store_bf16_32(du, dxv);
-            store_bf16_32(du + 64, dgv);
-          }
+      const int row0 = mt * BM + q * 32;
+      // the previous tile's TMA stores must have finished reading this warp's staging area
+      if (lane == 0) bulk_wait_group_read0();
+      __syncwarp();
+      if (has_aux && lane == 0) {
+        mbar_expect_tx(xbar, 8192);
+        if (p.mode == MCA_EPI_RESID) {  // fp32 boxes [32 cols x 32 rows]
+          tma_load_2d(stg, &tmAux, xbar, n0 + hf * 64, row0);
+          tma_load_2d(stg + 4096, &tmAux, xbar, n0 + hf * 64 + 32, row0);
+        } else {  // bf16 boxes [64 cols x 32 rows]: value-side and gate-side factors of this 64-column block
+          const int blk = (n0 + hf * 64) / 64;
+          tma_load_2d(stg, &tmAux, xbar, blk * 128, row0);
+          tma_load_2d(stg + 4096, &tmAux, xbar, blk * 128 + 64, row0);
         }
       }
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      uint32_t r0[32], r1[32];
+      if (p.mode == MCA_EPI_GEGLU) {  // tile columns are [64 value | 64 gate]
+        tmem_ld32(t_row + hf * 32, r0);
+        tmem_ld32(t_row + 64 + hf * 32, r1);
+      } else {
+        tmem_ld32(t_row + hf * 64, r0);
+        tmem_ld32(t_row + hf * 64 + 32, r1);
+      }
+      tmem_ld_wait();
+      // accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == 2) as = 0, aph ^= 1;
+
+      if (p.mode == MCA_EPI_BF16) {
+        const int ncol = n0 + hf * 64;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = c * 8 + i;
+            v[i] = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]) * p.alpha;
+            if (p.bias != nullptr && ncol + j < p.N) v[i] += __ldg(p.bias + ncol + j);
+          }
+          *reinterpret_cast<uint4*>(stg + sw128_off(lane, c)) = pack8(v);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO0, stg, ncol, row0);
+          bulk_commit_group();
+        }
+      } else if (p.mode == MCA_EPI_F32 || p.mode == MCA_EPI_RESID) {
+        if (has_aux) {
+          mbar_wait(xbar, xph);
+          xph ^= 1;
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int ncol = n0 + hf * 64 + b * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 v;
+            const uint32_t* r = b == 0 ? r0 : r1;
+            v.x = __uint_as_float(r[4 * c + 0]) * p.alpha, v.y = __uint_as_float(r[4 * c + 1]) * p.alpha;
+            v.z = __uint_as_float(r[4 * c + 2]) * p.alpha, v.w = __uint_as_float(r[4 * c + 3]) * p.alpha;
+            if (p.bias != nullptr && ncol + 4 * c < p.N) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + 4 * c));
+              v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(stg + b * 4096 + sw128_off(lane, c));
+            if (has_aux) {
+              const float4 a = *dst;
+              v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
+            }
+            *dst = v;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO0, stg, n0 + hf * 64, row0, z);
+          tma_store_3d(&tmO0, stg + 4096, n0 + hf * 64 + 32, row0, z);
+          bulk_commit_group();
+        }
+      } else if (p.mode == MCA_EPI_GEGLU) {
+        // r0 = value x, r1 = gate g for 32 (x, g) pairs.  Stored for the backward: a = gelu(g), bv = x * gelu'(g);
+        // forward output h = x * gelu(g).  Boxes of [32 cols x 32 rows] bf16 (64-byte rows, 64B swizzle).
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float av[8], bv[8], hv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = __uint_as_float(r0[c * 8 + i]), g = __uint_as_float(r1[c * 8 + i]);
+            float cdf, pdf;
+            gelu_cdf_pdf(g, cdf, pdf);
+            const float ge = g * cdf;
+            av[i] = ge;
+            bv[i] = x * fmaf(g, pdf, cdf);
+            hv[i] = x * ge;
+          }
+          const uint32_t o = sw64_off(lane, c);
+          *reinterpret_cast<uint4*>(stg + o) = pack8(av);
+          *reinterpret_cast<uint4*>(stg + 2048 + o) = pack8(bv);
+          *reinterpret_cast<uint4*>(stg + 4096 + o) = pack8(hv);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO1, stg, n0 + hf * 32, row0);
+          tma_store_2d(&tmO1, stg + 2048, n0 + 64 + hf * 32, row0);
+          tma_store_2d(&tmO0, stg + 4096, (n0 / 128) * 64 + hf * 32, row0);
+          bulk_commit_group();
+        }
+      } else {  // MCA_EPI_GEGLU_BWD: acc = dL/dh for 64 h-columns; staged (a | bv) are overwritten by (dL/dx | dL/dg)
+        mbar_wait(xbar, xph);
+        xph ^= 1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float a[8], b[8];
+          uint4* pa = reinterpret_cast<uint4*>(stg + sw128_off(lane, c));
+          uint4* pb = reinterpret_cast<uint4*>(stg + 4096 + sw128_off(lane, c));
+          unpack8(*pa, a);
+          unpack8(*pb, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = c * 8 + i;
+            const float d = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]) * p.alpha;
+            a[i] *= d;
+            b[i] *= d;
+          }
+          *pa = pack8(a);
+          *pb = pack8(b);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int blk = (n0 + hf * 64) / 64;
+          tma_store_2d(&tmO0, stg, blk * 128, row0);
+          tma_store_2d(&tmO0, stg + 4096, blk * 128 + 64, row0);
+          bulk_commit_group();
+        }
+      }
     }
+    if (lane == 0) bulk_wait_group0();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+template <bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO0, const CUtensorMap& tmO1,
+                       const CUtensorMap& tmAux, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_tc_kernel<A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
       return MCA_ERR_CUDA;
     attr_set = true;
   }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tmA, tmB, tmO0, tmO1, tmAux, p);
   return cudaGetLastError() == cudaSuccess ? MCA_OK : MCA_ERR_CUDA;
 }
 
@@ -320,15 +367,14 @@ extern "C" int mca_gemm_bf16(const void* A, int a_mn_major, long long lda, const
                              float alpha, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0 || k_splits < 1 || (N % 32) != 0) return MCA_ERR_SHAPE;
+  if (mode < MCA_EPI_BF16 || mode > MCA_EPI_GEGLU_BWD || out0 == nullptr) return MCA_ERR_ARG;
   if (mode != MCA_EPI_F32 && k_splits != 1) return MCA_ERR_SHAPE;
-  const int kb_total = (K + BK - 1) / BK;
-  if (k_splits > kb_total) k_splits = kb_total;
-  {  // every split must own at least one k-block
-    const int per = (kb_total + k_splits - 1) / k_splits;
-    k_splits = (kb_total + per - 1) / per;
-  }
-  const int BN = 128;
-  CUtensorMap tmA, tmB;
+  if ((mode == MCA_EPI_GEGLU && (out1 == nullptr || (N % 128) != 0)) ||
+      ((mode == MCA_EPI_RESID || mode == MCA_EPI_GEGLU_BWD) && aux0 == nullptr) ||
+      (mode == MCA_EPI_GEGLU_BWD && (N % 64) != 0))
+    return MCA_ERR_ARG;
+  k_splits = gemm_effective_splits(K, k_splits);  // every split owns at least one k-block
+  CUtensorMap tmA, tmB, tmO0, tmO1, tmAux;
   int rc;
   // K-major: global [rows, K] (K contiguous), box {64 k, rows}.  MN-major: global [K, rows] (rows contiguous), box {64 rows, 64 k}.
   rc = a_mn_major ? make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK)
@@ -337,12 +383,45 @@ extern "C" int mca_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   rc = b_mn_major ? make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK)
                   : make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
   if (rc != MCA_OK) return rc;
+  // epilogue maps: one box = what one epilogue warp stages (32 rows x 128 B, or x 64 B for the GEGLU outputs)
+  const uint64_t uM = (uint64_t)M, uN = (uint64_t)N;
+  if (mode == MCA_EPI_BF16) {
+    const uint64_t dims[2] = {uN, uM}, st[1] = {(uint64_t)ld0};
+    const uint32_t box[2] = {64, 32};
+    rc = make_tmap(&tmO0, 2, out0, 2, dims, st, box, 128);
+  } else if (mode == MCA_EPI_F32 || mode == MCA_EPI_RESID) {
+    const uint64_t dims[3] = {uN, uM, (uint64_t)k_splits}, st[2] = {(uint64_t)ld0, uM * (uint64_t)ld0};
+    const uint32_t box[3] = {32, 32, 1};
+    rc = make_tmap(&tmO0, 4, out0, 3, dims, st, box, 128);
+  } else if (mode == MCA_EPI_GEGLU) {
+    const uint64_t dims0[2] = {uN / 2, uM}, st0[1] = {(uint64_t)ld0};
+    const uint64_t dims1[2] = {uN, uM}, st1[1] = {(uint64_t)ld1};
+    const uint32_t box[2] = {32, 32};
+    rc = make_tmap(&tmO0, 2, out0, 2, dims0, st0, box, 64);
+    if (rc == MCA_OK) rc = make_tmap(&tmO1, 2, out1, 2, dims1, st1, box, 64);
+  } else {  // GEGLU_BWD: du has 2N columns
+    const uint64_t dims[2] = {2 * uN, uM}, st[1] = {(uint64_t)ld0};
+    const uint32_t box[2] = {64, 32};
+    rc = make_tmap(&tmO0, 2, out0, 2, dims, st, box, 128);
+  }
+  if (rc != MCA_OK) return rc;
+  if (mode != MCA_EPI_GEGLU) tmO1 = tmO0;
+  if (mode == MCA_EPI_RESID) {
+    const uint64_t dims[2] = {uN, uM}, st[1] = {(uint64_t)ldaux};
+    const uint32_t box[2] = {32, 32};
+    rc = make_tmap(&tmAux, 4, aux0, 2, dims, st, box, 128);
+  } else if (mode == MCA_EPI_GEGLU_BWD) {
+    const uint64_t dims[2] = {2 * uN, uM}, st[1] = {(uint64_t)ldaux};
+    const uint32_t box[2] = {64, 32};
+    rc = make_tmap(&tmAux, 2, aux0, 2, dims, st, box, 128);
+  } else {
+    tmAux = tmO0;
+  }
+  if (rc != MCA_OK) return rc;
   GemmParams p;
-  p.M = M, p.N = N, p.K = K, p.k_splits = k_splits, p.mode = mode;
-  p.out0 = out0, p.ld0 = ld0, p.out1 = out1, p.ld1 = ld1, p.aux0 = aux0, p.ldaux = ldaux, p.bias = bias;
-  p.alpha = alpha;
-  if (!a_mn_major && !b_mn_major) return launch_gemm<128, false, false>(tmA, tmB, p, stream);
-  if (!a_mn_major && b_mn_major) return launch_gemm<128, false, true>(tmA, tmB, p, stream);
-  if (a_mn_major && b_mn_major) return launch_gemm<128, true, true>(tmA, tmB, p, stream);
-  return launch_gemm<128, true, false>(tmA, tmB, p, stream);
+  p.M = M, p.N = N, p.K = K, p.k_splits = k_splits, p.mode = mode, p.bias = bias, p.alpha = alpha;
+  if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(tmA, tmB, tmO0, tmO1, tmAux, p, stream);
+  if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(tmA, tmB, tmO0, tmO1, tmAux, p, stream);
+  if (a_mn_major && b_mn_major) return launch_gemm<true, true>(tmA, tmB, tmO0, tmO1, tmAux, p, stream);
+  return launch_gemm<true, false>(tmA, tmB, tmO0, tmO1, tmAux, p, stream);
 }

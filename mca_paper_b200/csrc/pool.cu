@@ -144,33 +144,63 @@ pool_bwd_scores_kernel(const float* __restrict__ dout, const __nv_bfloat16* __re
 }
 
 // dK[b,j,h,:] = sum_r dS[b,h,r,j] qp[r,h,:] ; dV[b,j,h,:] = sum_r P[b,h,r,j] dout[b,r,h,:]   -> bf16 [B*N, 2*H*64]
+// and, fused, this key chunk's share of dqp[r,h,:] = sum_b sum_j dS[b,h,r,j] K[b,j,h,:] (one atomicAdd per output
+// per block; dqp must be zeroed by the launcher).
 // grid = (ceil(N/64), H, B), block 256: thread = (key j_local = t%64, 16-wide dim group = t/64)
 __global__ void __launch_bounds__(256)
 pool_bwd_kv_kernel(const float* __restrict__ ds, const float* __restrict__ probs, const float* __restrict__ qp,
-                   const float* __restrict__ dout, __nv_bfloat16* __restrict__ dkv, int B, int H, int R, int N) {
-  extern __shared__ float sm[];  // qs[R][64], gs[R][64]
+                   const float* __restrict__ dout, const __nv_bfloat16* __restrict__ kv, __nv_bfloat16* __restrict__ dkv,
+                   float* __restrict__ dqp, int B, int H, int R, int N) {
+  extern __shared__ float sm[];  // qs[R][64], gs[R][64], dsT[R][64], kt[64][65]
   float* qs = sm;
-  float* gs = sm + R * DH;
+  float* gs = qs + R * DH;
+  float* dss = gs + R * DH;
+  float* kt = dss + R * 64;
   const int h = blockIdx.y, b = blockIdx.z;
+  const int ld = 2 * H * DH;
+  const int j0 = blockIdx.x * 64;
   for (int i = threadIdx.x; i < R * DH; i += blockDim.x) {
     const int r = i / DH, c = i % DH;
     qs[i] = qp[r * H * DH + h * DH + c];
     gs[i] = dout[(static_cast<long long>(b) * R + r) * H * DH + h * DH + c];
+    const int jj = j0 + c;  // c doubles as the key index inside the chunk
+    dss[i] = jj < N ? ds[(static_cast<long long>(b * H + h) * R + r) * N + jj] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {  // K chunk: 64 keys x 64 dims, 16-byte loads
+    const int jl = i / 8, q8 = i % 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (j0 + jl < N) {
+      const uint4 q = *reinterpret_cast<const uint4*>(kv + (static_cast<long long>(b) * N + j0 + jl) * ld + h * DH + q8 * 8);
+      v[0] = bf16_lo(q.x), v[1] = bf16_hi(q.x), v[2] = bf16_lo(q.y), v[3] = bf16_hi(q.y);
+      v[4] = bf16_lo(q.z), v[5] = bf16_hi(q.z), v[6] = bf16_lo(q.w), v[7] = bf16_hi(q.w);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) kt[jl * 65 + q8 * 8 + e] = v[e];
   }
   __syncthreads();
-  const int j = blockIdx.x * 64 + (threadIdx.x % 64);
+  // ---- dqp partial: thread = (dim c = t%64, row group t/64 handles rows rg, rg+4, ...)
+  {
+    const int c = threadIdx.x % 64, rg = threadIdx.x / 64;
+    for (int r = rg; r < R; r += 4) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int jl = 0; jl < 64; ++jl) acc += dss[r * 64 + jl] * kt[jl * 65 + c];
+      if (acc != 0.f) atomicAdd(dqp + r * H * DH + h * DH + c, acc);
+    }
+  }
+  const int jl = threadIdx.x % 64;
+  const int j = j0 + jl;
   const int c0 = (threadIdx.x / 64) * 16;
   if (j >= N) return;
   float ak[16], av[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) ak[i] = 0.f, av[i] = 0.f;
   for (int r = 0; r < R; ++r) {
-    const long long o = (static_cast<long long>(b * H + h) * R + r) * N + j;
-    const float s = ds[o], p = probs[o];
+    const float s = dss[r * 64 + jl];
+    const float p = probs[(static_cast<long long>(b * H + h) * R + r) * N + j];
 #pragma unroll
     for (int i = 0; i < 16; ++i) ak[i] += s * qs[r * DH + c0 + i], av[i] += p * gs[r * DH + c0 + i];
   }
-  const int ld = 2 * H * DH;
   __nv_bfloat16* ok = dkv + (static_cast<long long>(b) * N + j) * ld + h * DH + c0;
   __nv_bfloat16* ov = ok + H * DH;
   uint4 q0, q1;
@@ -184,29 +214,6 @@ pool_bwd_kv_kernel(const float* __restrict__ ds, const float* __restrict__ probs
   q1.x = pack_bf16x2(av[8], av[9]), q1.y = pack_bf16x2(av[10], av[11]), q1.z = pack_bf16x2(av[12], av[13]),
   q1.w = pack_bf16x2(av[14], av[15]);
   reinterpret_cast<uint4*>(ov)[0] = q0, reinterpret_cast<uint4*>(ov)[1] = q1;
-}
-
-// dqp[r, h, :] = sum_b sum_j dS[b,h,r,j] K[b,j,h,:]   grid = H*R, block 256 (thread = (dim c = t%64, group t/64))
-__global__ void __launch_bounds__(256)
-pool_bwd_q_kernel(const float* __restrict__ ds, const __nv_bfloat16* __restrict__ kv, float* __restrict__ dqp, int B,
-                  int H, int R, int N) {
-  __shared__ float part[4][DH];
-  const int r = blockIdx.x % R, h = blockIdx.x / R;
-  const int c = threadIdx.x % DH, grp = threadIdx.x / DH;
-  const int ld = 2 * H * DH;
-  float acc = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float* drow = ds + (static_cast<long long>(b * H + h) * R + r) * N;
-    for (int j = grp; j < N; j += 4) {
-      const float s = drow[j];
-      if (s != 0.f) acc += s * __bfloat162float(kv[(static_cast<long long>(b) * N + j) * ld + h * DH + c]);
-    }
-  }
-  part[grp][c] = acc;
-  __syncthreads();
-  if (threadIdx.x < DH)
-    dqp[r * H * DH + h * DH + threadIdx.x] =
-        part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
 }
 
 // ---- tiny fp32 GEMM: C[m,n] = alpha * sum_k A(m,k) B(n,k) (+ C if accumulate) (+ add[m,n]); arbitrary strides
@@ -269,9 +276,11 @@ extern "C" int mca_pool_attn_bwd(const float* dout, const float* qp, const void*
   pool_bwd_scores_kernel<<<B * H * R, 256, N * sizeof(float), stream>>>(dout, kvb, probs, full_masked, ds_scratch, B, H,
                                                                         R, N);
   dim3 g2((N + 63) / 64, H, B);
-  pool_bwd_kv_kernel<<<g2, 256, 2 * R * DH * sizeof(float), stream>>>(ds_scratch, probs, qp, dout,
-                                                                      reinterpret_cast<__nv_bfloat16*>(dkv), B, H, R, N);
-  pool_bwd_q_kernel<<<H * R, 256, 0, stream>>>(ds_scratch, kvb, dqp, B, H, R, N);
+  if (cudaMemsetAsync(dqp, 0, static_cast<size_t>(R) * H * DH * sizeof(float), stream) != cudaSuccess) return MCA_ERR_CUDA;
+  const size_t sm2 = (3 * static_cast<size_t>(R) * DH + 64 * 65) * sizeof(float);
+  if (sm2 > 48 * 1024) return MCA_ERR_SHAPE;  // R <= 42
+  pool_bwd_kv_kernel<<<g2, 256, sm2, stream>>>(ds_scratch, probs, qp, dout, kvb, reinterpret_cast<__nv_bfloat16*>(dkv),
+                                               dqp, B, H, R, N);
   return check_launch();
 }
 

@@ -59,6 +59,30 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t
   return r == CUDA_SUCCESS ? MCA_OK : MCA_ERR_CUDA;
 }
 
+int make_tmap(CUtensorMap* out, int elem_bytes, const void* ptr, int rank, const uint64_t* dims,
+              const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes) {
+  auto fn = encode_fn();
+  if (fn == nullptr) return MCA_ERR_CUDA;
+  if (rank < 1 || rank > 3 || (elem_bytes != 2 && elem_bytes != 4)) return MCA_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return MCA_ERR_ALIGN;
+  cuuint64_t d[3] = {1, 1, 1};
+  cuuint64_t st[2] = {0, 0};
+  cuuint32_t bx[3] = {1, 1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) d[i] = dims[i], bx[i] = box[i];
+  for (int i = 0; i + 1 < rank; ++i) {
+    st[i] = strides_elems[i] * static_cast<uint64_t>(elem_bytes);
+    if (st[i] % 16 != 0) return MCA_ERR_ALIGN;
+  }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                  const_cast<void*>(ptr), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MCA_OK : MCA_ERR_CUDA;
+}
+
 }  // namespace mca
 
 extern "C" int mca_version(void) { return 100; }

@@ -20,6 +20,11 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
 int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride,
                      uint32_t box_inner, uint32_t box_outer);
 
+// general form: rank <= 3, elem_bytes 2 (bf16) or 4 (fp32); strides_elems[i] = stride of dim i+1 in elements;
+// swizzle_bytes 0 / 64 / 128 (box[0] * elem_bytes must not exceed it when non-zero)
+int make_tmap(CUtensorMap* out, int elem_bytes, const void* ptr, int rank, const uint64_t* dims,
+              const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
+
 inline int gemm_effective_splits(int K, int k_splits) {
   const int kb_total = (K + 63) / 64;
   if (k_splits < 1) k_splits = 1;

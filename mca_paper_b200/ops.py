@@ -79,7 +79,7 @@ def S():
 
 
 # kernels launched by each entry point (memsets not counted) — bench.py reports the per-step total
-KERNELS_PER_CALL = {"mca_build_offsets": 2, "mca_attn_fwd": 2, "mca_attn_bwd": 3, "mca_pool_attn_bwd": 3,
+KERNELS_PER_CALL = {"mca_build_offsets": 2, "mca_attn_fwd": 2, "mca_attn_bwd": 3, "mca_pool_attn_bwd": 2,
                     "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3}
 COUNT = {"n": 0}
 PROFILE = {"on": False, "events": []}

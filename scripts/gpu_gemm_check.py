@@ -8,14 +8,15 @@ lib = L.lib()
 dev = "cuda"
 torch.manual_seed(0)
 
-def gemm(A, a_mn, B, b_mn, M, N, K, mode, out0, out1=None, aux0=None, bias=None, alpha=1.0, splits=1):
+def gemm(A, a_mn, B, b_mn, M, N, K, mode, out0, out1=None, aux0=None, bias=None, alpha=1.0, splits=1, sync=True):
     rc = lib.mca_gemm_bf16(L.ptr(A), a_mn, ctypes.c_longlong(A.stride(0)), L.ptr(B), b_mn, ctypes.c_longlong(B.stride(0)),
                            M, N, K, splits, mode, L.ptr(out0), ctypes.c_longlong(out0.stride(-2)),
                            L.ptr(out1), ctypes.c_longlong(out1.stride(0) if out1 is not None else 0),
                            L.ptr(aux0), ctypes.c_longlong(aux0.stride(0) if aux0 is not None else 0),
                            L.ptr(bias), ctypes.c_float(alpha), L.stream_ptr())
     L.check(rc, "gemm")
-    torch.cuda.synchronize()
+    if sync:
+        torch.cuda.synchronize()
 
 def rel(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
@@ -44,7 +45,7 @@ for (M, N, K) in [(256, 128, 64), (1000, 512, 512), (20304, 1536, 512), (20304, 
     gemm(A, 0, B, 0, M, N, K, L.EPI_F32, o32, bias=bias, alpha=0.5); report(f"f32 bias alpha {M}x{N}x{K}", rel(o32[0], 0.5 * ref + bias), 1e-5)
     # residual
     res = torch.randn(M, N, device=dev); o2 = torch.zeros(M, N, device=dev); o2b = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-    gemm(A, 0, B, 0, M, N, K, L.EPI_RESID, o2, out1=o2b, aux0=res); report(f"resid {M}x{N}x{K}", rel(o2, ref + res), 1e-5); report(f"resid bf16 copy", rel(o2b, ref + res))
+    gemm(A, 0, B, 0, M, N, K, L.EPI_RESID, o2, aux0=res); report(f"resid {M}x{N}x{K}", rel(o2, ref + res), 1e-5)
 
 # split-K dW shape: dW[N_w, K_w] = dY^T X, tokens = 20304
 T = 20304
@@ -68,18 +69,17 @@ W1i = W1i.bfloat16()
 u = torch.zeros(M, 2 * IP, device=dev, dtype=torch.bfloat16); h = torch.zeros(M, IP, device=dev, dtype=torch.bfloat16)
 gemm(x, 0, W1i, 0, M, 2 * IP, D, L.EPI_GEGLU, h, out1=u)
 uref = x.float() @ W1i.float().t()
-report("geglu u", rel(u, uref))
-val = u.float()[:, rows_v]; gate = u.float()[:, rows_g]
+val = uref[:, rows_v].clone().requires_grad_(True); gate = uref[:, rows_g].clone().requires_grad_(True)
 href = torch.nn.functional.gelu(gate) * val
 report("geglu h", rel(h, href))
+report("geglu a=gelu(g)", rel(u.float()[:, rows_v], torch.nn.functional.gelu(gate)))
 # bwd: dh = dx4 @ W2 (B MN-major = W2 stored [D, IP])
 W2 = (torch.randn(D, IP, device=dev) * 0.05).bfloat16(); dx4 = torch.randn(M, D, device=dev).bfloat16()
 du = torch.zeros(M, 2 * IP, device=dev, dtype=torch.bfloat16)
 gemm(dx4, 0, W2, 1, M, IP, D, L.EPI_GEGLU_BWD, du, aux0=u)
 dh = dx4.float() @ W2.float()
-g = gate.clone().requires_grad_(True); v = val.clone().requires_grad_(True)
-(torch.nn.functional.gelu(g) * v).backward(dh)
-report("geglu bwd dval", rel(du.float()[:, rows_v], v.grad)); report("geglu bwd dgate", rel(du.float()[:, rows_g], g.grad))
+href.backward(dh)
+report("geglu bwd dval", rel(du.float()[:, rows_v], val.grad)); report("geglu bwd dgate", rel(du.float()[:, rows_g], gate.grad))
 
 # timing of the main shapes
 def bench(fn, n=20):
@@ -90,8 +90,23 @@ def bench(fn, n=20):
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n
 for (M, N, K) in [(20304, 1536, 512), (20304, 2816, 512), (20304, 512, 1408), (20304, 512, 512)]:
     A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16(); out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-    ms = bench(lambda: gemm(A, 0, B, 0, M, N, K, L.EPI_BF16, out))
+    ms = bench(lambda: gemm(A, 0, B, 0, M, N, K, L.EPI_BF16, out, sync=False))
     ms_t = bench(lambda: torch.matmul(A, B.t()))
-    print(f"time {M}x{N}x{K}: ours {ms*1e3:.1f} us ({2*M*N*K/ms/1e9:.0f} TFLOP/s)  torch {ms_t*1e3:.1f} us ({2*M*N*K/ms_t/1e9:.0f} TFLOP/s)", flush=True)
+    print(f"time bf16 {M}x{N}x{K}: ours {ms*1e3:.1f} us ({2*M*N*K/ms/1e9:.0f} TFLOP/s)  torch {ms_t*1e3:.1f} us ({2*M*N*K/ms_t/1e9:.0f} TFLOP/s)", flush=True)
+    if N == 512:
+        res = torch.randn(M, N, device=dev); o2 = torch.zeros(M, N, device=dev)
+        ms = bench(lambda: gemm(A, 0, B, 0, M, N, K, L.EPI_RESID, o2, aux0=res, sync=False))
+        print(f"time resid {M}x{N}x{K}: ours {ms*1e3:.1f} us ({2*M*N*K/ms/1e9:.0f} TFLOP/s, {(M*K*2+2*M*N*4)/ms/1e6:.0f} GB/s)", flush=True)
+M = 20304
+x = torch.randn(M, D, device=dev).bfloat16(); u = torch.zeros(M, 2 * IP, device=dev, dtype=torch.bfloat16); h = torch.zeros(M, IP, device=dev, dtype=torch.bfloat16)
+ms = bench(lambda: gemm(x, 0, W1i, 0, M, 2 * IP, D, L.EPI_GEGLU, h, out1=u, sync=False))
+print(f"time geglu fwd {M}x{2*IP}x{D}: {ms*1e3:.1f} us ({2*M*2*IP*D/ms/1e9:.0f} TFLOP/s)", flush=True)
+dx4 = torch.randn(M, D, device=dev).bfloat16(); du = torch.zeros(M, 2 * IP, device=dev, dtype=torch.bfloat16)
+ms = bench(lambda: gemm(dx4, 0, W2, 1, M, IP, D, L.EPI_GEGLU_BWD, du, aux0=u, sync=False))
+print(f"time geglu bwd {M}x{IP}x{D}: {ms*1e3:.1f} us ({2*M*IP*D/ms/1e9:.0f} TFLOP/s)", flush=True)
+dY = torch.randn(M, 2816, device=dev).bfloat16(); X = torch.randn(M, 512, device=dev).bfloat16()
+eff = lib.mca_gemm_effective_splits(M, 3); part = torch.zeros(eff, 2816, 512, device=dev)
+ms = bench(lambda: gemm(dY, 1, X, 1, 2816, 512, M, L.EPI_F32, part, splits=3, sync=False))
+print(f"time dW 2816x512x{M} splitK={eff}: {ms*1e3:.1f} us ({2*M*2816*512/ms/1e9:.0f} TFLOP/s)", flush=True)
 print("ALL OK" if ok else "SOME FAILED")
 sys.exit(0 if ok else 1)

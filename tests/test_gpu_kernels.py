@@ -60,10 +60,14 @@ def test_gemm_residual_and_geglu_epilogues():
     res = torch.randn(M, D, device=dev)
     o = torch.zeros(M, D, device=dev)
     ob = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
-    ops.gemm(x, 0, W, 0, M, D, D, L.EPI_RESID, o, out1=ob, ld1=D, aux0=res, ldaux=D)
+    ops.gemm(x, 0, W, 0, M, D, D, L.EPI_RESID, o, aux0=res, ldaux=D)
     ref = x.float() @ W.float().t() + res
-    assert rel_err(o, ref) < 1e-5 and rel_err(ob, ref) < 5e-3
-    # GEGLU with interleaved W1 (64 value rows | 64 gate rows per 128 block), exact erf GELU (model.py:35-38)
+    assert rel_err(o, ref) < 1e-5
+    ops.gemm(x, 0, W, 0, M, D, D, L.EPI_BF16, ob)
+    assert rel_err(ob, x.float() @ W.float().t()) < 5e-3
+    # GEGLU with interleaved W1 (64 value rows | 64 gate rows per 128 block), exact erf GELU (model.py:35-38).
+    # The epilogue stores, per (value x, gate g) pair, the two factors the backward needs: a = gelu(g) in the value
+    # slot and bv = x * gelu'(g) in the gate slot; h = x * gelu(g) is the forward output.
     W1 = torch.randn(2 * I, D, device=dev) * 0.05
     W1i = torch.zeros(2 * IP, D, device=dev)
     v = torch.arange(IP, device=dev)
@@ -76,18 +80,18 @@ def test_gemm_residual_and_geglu_epilogues():
     h = torch.zeros(M, IP, device=dev, dtype=torch.bfloat16)
     ops.gemm(x, 0, W1i, 0, M, 2 * IP, D, L.EPI_GEGLU, h, ld0=IP, out1=u, ld1=2 * IP)
     uref = x.float() @ W1i.float().t()
-    assert rel_err(u, uref) < 5e-3
-    val, gate = u.float()[:, rows_v], u.float()[:, rows_g]
-    assert rel_err(h, torch.nn.functional.gelu(gate) * val) < 5e-3
+    val = uref[:, rows_v].clone().requires_grad_(True)
+    gate = uref[:, rows_g].clone().requires_grad_(True)
+    href = torch.nn.functional.gelu(gate) * val
+    assert rel_err(h, href) < 5e-3
     assert (h[:, I:] == 0).all()                                   # zero padding of the odd inner dim is exact
+    assert rel_err(u.float()[:, rows_v], torch.nn.functional.gelu(gate)) < 5e-3
     W2 = (torch.randn(D, IP, device=dev) * 0.05).bfloat16()
     dy = torch.randn(M, D, device=dev).bfloat16()
     du = torch.zeros(M, 2 * IP, device=dev, dtype=torch.bfloat16)
     ops.gemm(dy, 0, W2, 1, M, IP, D, L.EPI_GEGLU_BWD, du, ld0=2 * IP, aux0=u, ldaux=2 * IP)
-    g = gate.clone().requires_grad_(True)
-    vv = val.clone().requires_grad_(True)
-    (torch.nn.functional.gelu(g) * vv).backward(dy.float() @ W2.float())
-    assert rel_err(du.float()[:, rows_v], vv.grad) < 5e-3 and rel_err(du.float()[:, rows_g], g.grad) < 5e-3
+    href.backward(dy.float() @ W2.float())
+    assert rel_err(du.float()[:, rows_v], val.grad) < 1e-2 and rel_err(du.float()[:, rows_g], gate.grad) < 1e-2
 
 
 def test_gemm_rejects_bad_shapes():
