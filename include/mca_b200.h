@@ -92,11 +92,12 @@ int mca_gemm_effective_splits(int K, int k_splits);
  * Outputs: padding [B,N] bytes (== reference `padding`), pad_mod (per-modality [B,len] bytes, modality-major),
  * present [B,n_mod] (== modality_sample_mask, model.py:458), live_count [B,n_mod], live_idx [B,N] (packed varlen
  * gather indices: live positions of each modality in order, -1 filled), cu_live [B*n_mod+1] (exclusive cumsum),
- * kt_class [B,n_kt] (0 all keys live, 1 mixed, 2 all padded -> tile skipped), any_absent (1 int). */
+ * kt_class [B,n_kt] (0 all keys live, 1 mixed, 2 all padded -> tile skipped), kt_live [B,n_kt,4] (bit j of the
+ * 128-bit word = key j of the tile exists and is not padded), any_absent (1 int). */
 int mca_build_offsets(const void* const* masks_host, const int* elem_sizes_host, const int* lens_host, int n_mod,
                       int B, int N, const int* kt_start, const int* kt_len, int n_kt, uint8_t* padding,
                       uint8_t* pad_mod, uint8_t* present, int* live_count, int* live_idx, int* cu_live,
-                      uint8_t* kt_class, int* any_absent, void* stream);
+                      uint8_t* kt_class, uint32_t* kt_live, int* any_absent, void* stream);
 
 /* LayerNorm over d = 512 (model.py:24-31; eps 1e-5).  Optional: pad [rows] bytes -> zero output (encoders.py:205),
  * pe [seg_len,512] added after (encoders.py:208-209), row scatter out_row = (r/seg_len)*out_rows_per_b + out_row_off
@@ -137,11 +138,13 @@ int mca_cast_f32_bf16(const float* src, long long ld_src, void* dst, long long l
                       void* stream);
 
 /* Block-sparse masked multi-head attention (model.py:85-100), dim_head = 64.  qkv: bf16 [B*N, 3*H*64] = (Q*scale | K | V),
- * out: bf16 [B*N, H*64], lse: [B,H,N] natural-log row log-sum-exp (+inf marks a fully masked row). */
+ * out: bf16 [B*N, H*64], lse: [B,H,N] natural-log row log-sum-exp (+inf marks a fully masked row).
+ * q_tiles may be listed in any order (heaviest first balances the SMs); tile_grp[n_kt] = key group shared by all
+ * keys of the tile or 255 when the tile mixes groups; kt_live = live-key bit words from mca_build_offsets. */
 int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int n_qt, const mca_attn_ref* kt_list,
                  const mca_attn_tile* k_tiles, int n_kt, const uint32_t* rowbits, const uint8_t* keygrp,
-                 const uint8_t* padding, const uint8_t* kt_class, const int* any_absent, float* vmean, void* out,
-                 float* lse, int B, int N, int H, void* stream);
+                 const uint8_t* tile_grp, const uint8_t* kt_class, const uint32_t* kt_live, const int* any_absent,
+                 float* vmean, void* out, float* lse, int B, int N, int H, void* stream);
 /* Backward: dout bf16 [B*N, H*64] -> dqkv bf16 [B*N, 3*H*64].  k_tiles_q lists, for every key tile, the query tiles
  * that attend it (transposed schedule).  dq_accum: fp32 [B*N, H*64] scratch, delta: [B,H,N], ucorr: [B, H*64]. */
 int mca_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const mca_attn_qtile* k_tiles_q,

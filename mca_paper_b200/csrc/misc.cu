@@ -71,16 +71,22 @@ offsets_kernel(OffsetsArgs a, uint8_t* __restrict__ padding, uint8_t* __restrict
 // second phase: per (sample, key tile) class 0 = all live, 1 = mixed, 2 = all padded; exclusive cumsum of counts
 __global__ void __launch_bounds__(128)
 offsets_tiles_kernel(const uint8_t* __restrict__ padding, const int* __restrict__ kt_start,
-                     const int* __restrict__ kt_len, int n_kt, uint8_t* __restrict__ kt_class, int B, int N,
-                     const int* __restrict__ live_count, int n_mod, int* __restrict__ cu_live) {
+                     const int* __restrict__ kt_len, int n_kt, uint8_t* __restrict__ kt_class,
+                     uint32_t* __restrict__ kt_live, int B, int N, const int* __restrict__ live_count, int n_mod,
+                     int* __restrict__ cu_live) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * n_kt) {
     const int b = i / n_kt, kt = i % n_kt;
     const uint8_t* p = padding + static_cast<long long>(b) * N + kt_start[kt];
     int npad = 0;
     const int len = kt_len[kt];
-    for (int j = 0; j < len; ++j) npad += p[j];
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int j = 0; j < len; ++j) {
+      npad += p[j] != 0;
+      if (p[j] == 0) w[j >> 5] |= 1u << (j & 31);
+    }
     kt_class[i] = npad == 0 ? 0 : (npad == len ? 2 : 1);
+    if (kt_live != nullptr) *reinterpret_cast<uint4*>(kt_live + static_cast<long long>(i) * 4) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   if (i == 0) {
     int acc = 0;
@@ -178,7 +184,7 @@ using namespace mca;
 extern "C" int mca_build_offsets(const void* const* masks_host, const int* elem_sizes_host, const int* lens_host,
                                  int n_mod, int B, int N, const int* kt_start, const int* kt_len, int n_kt,
                                  uint8_t* padding, uint8_t* pad_mod, uint8_t* present, int* live_count, int* live_idx,
-                                 int* cu_live, uint8_t* kt_class, int* any_absent, void* stream_) {
+                                 int* cu_live, uint8_t* kt_class, uint32_t* kt_live, int* any_absent, void* stream_) {
   if (n_mod <= 0 || n_mod > MCA_MAX_MODALITIES || B <= 0) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   OffsetsArgs a;
@@ -193,8 +199,8 @@ extern "C" int mca_build_offsets(const void* const* masks_host, const int* elem_
   if (cudaMemsetAsync(any_absent, 0, sizeof(int), stream) != cudaSuccess) return MCA_ERR_CUDA;
   offsets_kernel<<<B * n_mod, 32, 0, stream>>>(a, padding, pad_mod, present, live_count, live_idx, any_absent);
   const int n = B * n_kt > 1 ? B * n_kt : 1;
-  offsets_tiles_kernel<<<(n + 127) / 128, 128, 0, stream>>>(padding, kt_start, kt_len, n_kt, kt_class, B, N, live_count,
-                                                            n_mod, cu_live);
+  offsets_tiles_kernel<<<(n + 127) / 128, 128, 0, stream>>>(padding, kt_start, kt_len, n_kt, kt_class, kt_live, B, N,
+                                                            live_count, n_mod, cu_live);
   return check_launch();
 }
 

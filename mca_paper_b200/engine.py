@@ -100,7 +100,8 @@ class Engine:
         self.keygrp = t(pl.keygrp)
         self.rowbits = t(pl.rowbits.view(np.int32))
         self.pool_rowbits = t(pl.pool_rowbits.view(np.int32))
-        self.q_tiles = t(pl.q_tiles)
+        self.q_tiles = t(pl.q_tiles_sorted)
+        self.tile_grp = t(pl.tile_grp)
         self.kt_list = t(pl.kt_list)
         self.k_tiles = t(pl.tiles)
         self.k_tiles_q = t(pl.k_tiles_q)
@@ -203,6 +204,7 @@ class Engine:
         ws["present"], ws["live_count"] = u8(B, self.plan.n_mod), i32(B, self.plan.n_mod)
         ws["live_idx"], ws["cu_live"] = i32(B, N), i32(B * self.plan.n_mod + 1)
         ws["kt_class"], ws["any_absent"], ws["nonfinite"] = u8(B, self.n_kt), i32(1), i32(1)
+        ws["kt_live"] = i32(B, self.n_kt, 4)
         # encoders
         ws["enc"] = {}
         for name, enc in zip(self.plan.names, self.model.encoder_specs):
@@ -258,7 +260,7 @@ class Engine:
         call("mca_build_offsets", ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(es, ctypes.c_void_p),
              ctypes.cast(lens, ctypes.c_void_p), n, self.B, self.N, P(self.kt_start), P(self.kt_len), self.n_kt,
              P(ws["padding"]), P(ws["pad_mod"]), P(ws["present"]), P(ws["live_count"]), P(ws["live_idx"]),
-             P(ws["cu_live"]), P(ws["kt_class"]), P(ws["any_absent"]), S())
+             P(ws["cu_live"]), P(ws["kt_class"]), P(ws["kt_live"]), P(ws["any_absent"]), S())
 
     def _pad_mod(self, i):
         pl = self.plan
@@ -313,8 +315,8 @@ class Engine:
     def attention_fwd(self, qkv, out, lse):
         ws = self.ws
         call("mca_attn_fwd", P(qkv), P(self.q_tiles), int(self.q_tiles.shape[0]), P(self.kt_list), P(self.k_tiles),
-             self.n_kt, P(self.rowbits), P(self.keygrp), P(ws["padding"]), P(ws["kt_class"]), P(ws["any_absent"]),
-             P(ws["vmean"]), P(out), P(lse), self.B, self.N, self.H, S())
+             self.n_kt, P(self.rowbits), P(self.keygrp), P(self.tile_grp), P(ws["kt_class"]), P(ws["kt_live"]),
+             P(ws["any_absent"]), P(ws["vmean"]), P(out), P(lse), self.B, self.N, self.H, S())
 
     def trunk_forward(self, batch):
         """encoders -> depth x [LN, QKV, attention, out-proj(+res), LN, FF1(GEGLU), FF2(+res)] -> LN -> pooling."""

@@ -29,7 +29,7 @@ _SIGS = {
     "mca_version": [],
     "mca_gemm_effective_splits": [I32, I32],
     "mca_gemm_bf16": [VP, I32, I64, VP, I32, I64, I32, I32, I32, I32, I32, VP, I64, VP, I64, VP, I64, VP, F32, VP],
-    "mca_build_offsets": [VP, VP, VP, I32, I32, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP],
+    "mca_build_offsets": [VP, VP, VP, I32, I32, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP],
     "mca_layernorm512_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I64, VP],
     "mca_layernorm512_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I64, VP],
     "mca_layernorm_in_fwd": [VP, VP, VP, VP, VP, VP, I32, I32, I64, VP, VP],
@@ -40,7 +40,7 @@ _SIGS = {
     "mca_broadcast_rows": [VP, VP, I32, I32, I32, I32, I32, VP],
     "mca_batchsum_rows": [VP, VP, I32, I32, I32, I32, I32, I32, VP],
     "mca_cast_f32_bf16": [VP, I64, VP, I64, I64, I32, VP],
-    "mca_attn_fwd": [VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
+    "mca_attn_fwd": [VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
     "mca_attn_bwd": [VP, VP, VP, VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
     "mca_pool_attn_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
     "mca_pool_attn_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],

@@ -134,6 +134,15 @@ class StaticPlan:
                     pair[(qi, ki)] = flag
             q_rows.append((qs, ql, off, len(fwd_refs) - off))
         self.q_tiles = np.asarray(q_rows, dtype=np.int32).reshape(-1, 4)
+        # launch order of the forward kernel: heaviest query tiles first (longest-processing-time-first balancing)
+        order = np.argsort(-self.q_tiles[:, 3], kind="stable")
+        self.q_tiles_sorted = np.ascontiguousarray(self.q_tiles[order])
+        # key group shared by every key of a tile, 255 when the tile mixes groups (the fusion sub-blocks)
+        tg = []
+        for ks, kl in tiles:
+            g = np.unique(self.keygrp[ks:ks + kl])
+            tg.append(int(g[0]) if len(g) == 1 else 255)
+        self.tile_grp = np.asarray(tg, dtype=np.uint8)
         self.kt_list = np.asarray(fwd_refs, dtype=np.int32).reshape(-1, 2)
         bwd_refs, k_rows = [], []
         for ki, (ks, kl) in enumerate(tiles):
