@@ -149,8 +149,8 @@ int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int n_qt, const
  * that attend it (transposed schedule).  dq_accum: fp32 [B*N, H*64] scratch, delta: [B,H,N], ucorr: [B, H*64]. */
 int mca_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const mca_attn_qtile* k_tiles_q,
                  int n_kt, const mca_attn_ref* qt_list, const mca_attn_tile* q_tiles, int n_qt, const uint32_t* rowbits,
-                 const uint8_t* keygrp, const uint8_t* padding, const uint8_t* kt_class, float* delta, float* ucorr,
-                 float* dq_accum, void* dqkv, int B, int N, int H, void* stream);
+                 const uint8_t* keygrp, const uint8_t* tile_grp, const uint8_t* padding, const uint8_t* kt_class,
+                 float* delta, float* ucorr, float* dq_accum, void* dqkv, int B, int N, int H, void* stream);
 
 /* Attention pooling core (model.py:472-473): qp [R,H*64] fp32 scaled queries, kv bf16 [B*N, 2*H*64] (K|V),
  * rowbits[R] allowed key groups per pooled row, probs [B,H,R,N] saved for the backward, out [B,R,H*64]. */

@@ -433,7 +433,8 @@ class Engine:
         ws = self.ws
         call("mca_attn_bwd", P(ws["qkv"][l]), P(ws["ao"][l]), P(ws["dattn"]), P(ws["lse"][l]), P(self.k_tiles_q),
              self.n_kt, P(self.qt_list), P(self.k_tiles), int(self.q_tiles.shape[0]), P(self.rowbits), P(self.keygrp),
-             P(ws["padding"]), P(ws["kt_class"]), P(ws["delta"]), P(ws["ucorr"]), P(ws["dq_acc"]), P(ws["dqkv"]),
+             P(self.tile_grp), P(ws["padding"]), P(ws["kt_class"]), P(ws["delta"]), P(ws["ucorr"]), P(ws["dq_acc"]),
+             P(ws["dqkv"]),
              self.B, self.N, self.H, S())
 
     def encode_backward(self, dx0):

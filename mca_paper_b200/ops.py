@@ -41,7 +41,7 @@ _SIGS = {
     "mca_batchsum_rows": [VP, VP, I32, I32, I32, I32, I32, I32, VP],
     "mca_cast_f32_bf16": [VP, I64, VP, I64, I64, I32, VP],
     "mca_attn_fwd": [VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
-    "mca_attn_bwd": [VP, VP, VP, VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
+    "mca_attn_bwd": [VP, VP, VP, VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
     "mca_pool_attn_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
     "mca_pool_attn_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
     "mca_small_gemm_f32": [VP, I64, I64, VP, I64, I64, VP, I64, VP, I64, I32, I32, I32, F32, I32, VP],

@@ -186,8 +186,8 @@ def _attention_case(cfg, variant, scale):
     ws = eng.ws
     ws["dattn"].copy_(do)
     call("mca_attn_bwd", P(qkv), P(out), P(ws["dattn"]), P(lse), P(eng.k_tiles_q), eng.n_kt, P(eng.qt_list), P(eng.k_tiles),
-         int(eng.q_tiles.shape[0]), P(eng.rowbits), P(eng.keygrp), P(ws["padding"]), P(ws["kt_class"]), P(ws["delta"]),
-         P(ws["ucorr"]), P(ws["dq_acc"]), P(ws["dqkv"]), B, N, H, stream())
+         int(eng.q_tiles.shape[0]), P(eng.rowbits), P(eng.keygrp), P(eng.tile_grp), P(ws["padding"]), P(ws["kt_class"]),
+         P(ws["delta"]), P(ws["ucorr"]), P(ws["dq_acc"]), P(ws["dqkv"]), B, N, H, stream())
     gref = x.grad.view(M, 1536)
     d = ws["dqkv"].float()
     for sl in (slice(0, 512), slice(512, 1024), slice(1024, 1536)):
