@@ -25,12 +25,14 @@ namespace mca {
 
 constexpr int AB_T = 128;
 constexpr int AB_DH = 64;
-constexpr int AB_THREADS = 320;            // 2 compute warpgroups + TMA warp + MMA warp
+constexpr int AB_THREADS = 352;            // 2 compute warpgroups + TMA warp + MMA warp + dQ-reduce warp
 constexpr int AB_TILE = AB_T * AB_DH * 2;  // 16 KB bf16 [128, 64]
 constexpr int AB_DS = AB_T * AB_T * 2;     // 32 KB bf16 dS tile, stored [key][query] in two 64-query halves
 constexpr int AB_DQ = AB_T * AB_DH * 4;    // 32 KB fp32 [128, 64]
-// sK, sV, 2x(sQ, sdO), 2x sdS, sdQ, per-query staging + barriers
-constexpr int AB_SMEM = 2 * AB_TILE + 4 * AB_TILE + 2 * AB_DS + AB_DQ + 1024 /*align*/ + 4096;
+constexpr int AB_QSTAGES = 3;
+constexpr int AB_MAX_ITERS = 64;  // query tiles attending one key tile
+// sK, sV, 3x(sQ, sdO), sdS (half 0 double buffered, half 1 single), sdQ; per-query staging and barriers are static
+constexpr int AB_SMEM = 2 * AB_TILE + 2 * AB_QSTAGES * AB_TILE + 3 * (AB_DS / 2) + AB_DQ;
 constexpr float AB_LOG2E = 1.4426950408889634f;
 
 struct AttnBwdArgs {
@@ -51,29 +53,50 @@ struct AttnBwdArgs {
 
 __device__ __forceinline__ void ab_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+#ifdef MCA_TRACE
+// debug-only timeline (built with MCA_NVCC_EXTRA=-DMCA_TRACE): clock64 stamps of one CTA, read by mca_debug_read_trace
+__device__ long long g_trace[4 * 16 * 16 + 8];
+#define TR(role, t, e) do { if (blockIdx.x == 5 && blockIdx.y == 3 && (t) < 16) g_trace[((role) * 16 + (t)) * 16 + (e)] = clock64(); } while (0)
+#define TRG(e) do { if (blockIdx.x == 5 && blockIdx.y == 3) g_trace[4 * 16 * 16 + (e)] = clock64(); } while (0)
+#else
+#define TR(role, t, e) do { } while (0)
+#define TRG(e) do { } while (0)
+#endif
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_dq, const AttnBwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = base;
+  extern __shared__ __align__(1024) uint8_t smem[];  // kept in the shared address space: no generic-pointer casts
+  uint8_t* sK = smem;
   uint8_t* sV = sK + AB_TILE;
-  uint8_t* sQ = sV + AB_TILE;        // 2 stages
-  uint8_t* sdO = sQ + 2 * AB_TILE;   // 2 stages
-  uint8_t* sdS = sdO + 2 * AB_TILE;  // 2 buffers
-  uint8_t* sdQ = sdS + 2 * AB_DS;
-  float* s_lse = reinterpret_cast<float*>(sdQ + AB_DQ);  // [2 halves][2 buffers][64]
-  float* s_dl = s_lse + 256;
-  uint32_t* s_rb = reinterpret_cast<uint32_t*>(s_dl + 256);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rb + 256);
+  uint8_t* sQ = sV + AB_TILE;                 // AB_QSTAGES stages
+  uint8_t* sdO = sQ + AB_QSTAGES * AB_TILE;   // AB_QSTAGES stages
+  uint8_t* sdS = sdO + AB_QSTAGES * AB_TILE;  // [half 0, buffer 0][half 0, buffer 1][half 1], 16 KB each
+  uint8_t* sdQ = sdS + 3 * (AB_DS / 2);       // two 32-column fp32 boxes
+  __shared__ int2 s_qt[AB_MAX_ITERS];                 // (start, len) of every query tile this CTA visits
+  __shared__ __align__(16) float s_lse[2][2][64];     // [half][buffer][query]: -lse*log2e, -inf = masked
+  __shared__ __align__(16) float s_dl[2][2][64];      // -delta
+  __shared__ __align__(16) uint32_t s_rb[2][2][64];   // allowed-key-group bits (mixed-group tiles only)
+  __shared__ uint64_t bars[24];
+  __shared__ uint32_t tmem_holder_s;
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* x_full = bars + 5;     // [2] per half
-  uint64_t* c_done = bars + 7;     // [2] per half
-  uint64_t* z_full = bars + 9;     // [2] per dQ buffer
-  uint64_t* dq_free = bars + 11;   // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* qdo_full = bars + 1;   // [AB_QSTAGES]
+  uint64_t* qdo_empty = bars + 4;  // [AB_QSTAGES]
+  uint64_t* x_full = bars + 7;     // [2] per half: S^T / dP^T of the half are in TMEM
+  uint64_t* x_free = bars + 9;     // [2] per half: the compute warpgroup has copied them to registers
+  uint64_t* c_done = bars + 11;    // [2] per half: P^T / dS^T written (TMEM + smem)
+  uint64_t* y_done = bars + 13;    // dV / dK products of one half retired: the P^T / dS^T columns are free
+  uint64_t* z_full = bars + 14;    // [2] by tile parity: dQ product retired (dS consumed, dQ accumulator complete)
+  uint64_t* dq_free = bars + 16;   // dQ accumulator copied to registers
+  uint64_t* sdq_full = bars + 17;  // dQ tile staged in shared memory
+  uint64_t* sdq_free = bars + 18;  // the TMA reduce has finished reading the staged tile
+  uint32_t* tmem_holder = &tmem_holder_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % a.H, b = blockIdx.x / a.H;
@@ -89,107 +112,163 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dq);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&qdo_full[s], 1), mbar_init(&qdo_empty[s], 1);
-      mbar_init(&x_full[s], 1), mbar_init(&c_done[s], 128);
-      mbar_init(&z_full[s], 1), mbar_init(&dq_free[s], 128);
-    }
+    for (int s = 0; s < AB_QSTAGES; ++s) mbar_init(&qdo_full[s], 1), mbar_init(&qdo_empty[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&x_full[s], 1), mbar_init(&x_free[s], 128), mbar_init(&c_done[s], 128);
+    mbar_init(y_done, 1);
+    mbar_init(&z_full[0], 1), mbar_init(&z_full[1], 1);
+    mbar_init(dq_free, 128);
+    mbar_init(sdq_full, 128);
+    mbar_init(sdq_free, 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(tmem_holder, 512);
+  for (int i = threadIdx.x; i < n_iter; i += AB_THREADS) {
+    const mca_attn_tile Q = a.q_tiles[a.qt_list[KT.kt_off + i].tile];
+    s_qt[i] = make_int2(Q.start, Q.len);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  // region h: [S^T_h | dP^T_h] (64 + 64 fp32 columns), later [P^T_h (32) .. | dS^T_h (32) ..]
-  const uint32_t tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;  // tdQ: 2 x 64 columns
+  // columns: [0,128) S^T_0 | dP^T_0, [128,256) S^T_1 | dP^T_1, [256,320) P^T (32) | dS^T (32) of the half in flight,
+  //          [320,384) dV, [384,448) dK, [448,512) dQ
+  const uint32_t tP = tmem_base + 256, tdV = tmem_base + 320, tdK = tmem_base + 384, tdQ = tmem_base + 448;
+  if (threadIdx.x == 0) TRG(0);
 
   if (warp == 8) {
-    // ===================== TMA producer =====================
-    if (lane == 0 && n_iter > 0) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    if (n_iter > 0) {
       const int krow = static_cast<int>(row0 + KT.start);
-      mbar_expect_tx(kv_full, 2 * AB_TILE);
-      tma_load_2d(sK, &tm_qkv, kv_full, HD + h * AB_DH, krow);
-      tma_load_2d(sV, &tm_qkv, kv_full, 2 * HD + h * AB_DH, krow);
+      if (elect_one()) {
+        mbar_expect_tx(kv_full, 2 * AB_TILE);
+        tma_load_2d(sK, &tm_qkv, kv_full, HD + h * AB_DH, krow);
+        tma_load_2d(sV, &tm_qkv, kv_full, 2 * HD + h * AB_DH, krow);
+      }
+      __syncwarp();
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it & 1;
-        const uint32_t sph = (it >> 1) & 1;
-        const mca_attn_tile Q = a.q_tiles[a.qt_list[KT.kt_off + it].tile];
-        const int qrow = static_cast<int>(row0 + Q.start);
+        const int s = it % AB_QSTAGES;
+        const uint32_t sph = (it / AB_QSTAGES) & 1;
+        const int qrow = static_cast<int>(row0 + s_qt[it].x);
         mbar_wait(&qdo_empty[s], sph ^ 1);
-        mbar_expect_tx(&qdo_full[s], 2 * AB_TILE);
-        tma_load_2d(sQ + s * AB_TILE, &tm_qkv, &qdo_full[s], h * AB_DH, qrow);
-        tma_load_2d(sdO + s * AB_TILE, &tm_do, &qdo_full[s], h * AB_DH, qrow);
+        if (elect_one()) {
+          mbar_expect_tx(&qdo_full[s], 2 * AB_TILE);
+          tma_load_2d(sQ + s * AB_TILE, &tm_qkv, &qdo_full[s], h * AB_DH, qrow);
+          tma_load_2d(sdO + s * AB_TILE, &tm_do, &qdo_full[s], h * AB_DH, qrow);
+        }
+        __syncwarp();
       }
     }
+  } else if (warp == 10) {
+    // ===================== dQ reduce issuer: staged fp32 tile -> TMA reduce-add into dq_acc =====================
+    for (int t = 0; t < n_iter; ++t) {
+      const int qrow = static_cast<int>(row0 + s_qt[t].x);
+      mbar_wait(sdq_full, t & 1);
+      if (elect_one()) {  // same membermask every time -> same leader, which owns the bulk async-groups
+        tma_reduce_add_2d(&tm_dq, sdQ, h * AB_DH, qrow);
+        tma_reduce_add_2d(&tm_dq, sdQ + AB_DQ / 2, h * AB_DH + 32, qrow);
+        bulk_commit_group();
+        bulk_wait_group_read0();
+        mbar_arrive(sdq_free);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) bulk_wait_group0();
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && n_iter > 0) {
+    // The whole warp runs the loop and the waits (convergent code keeps the descriptors in uniform registers, so a
+    // tcgen05.mma costs one uniform add); one elected lane issues the MMAs and commits.  Independent accumulation
+    // chains are interleaved (S^T with dP^T, dV with dK).
+    if (n_iter > 0) {
       constexpr uint32_t id_x = make_idesc_bf16(AB_T, 64, false, false);    // S^T, dP^T: K-major x K-major, N = 64
       constexpr uint32_t id_y = make_idesc_bf16(AB_T, AB_DH, false, true);  // dV, dK: A from TMEM, B MN-major
       constexpr uint32_t id_z = make_idesc_bf16(AB_T, AB_DH, true, true);   // dQ: MN-major x MN-major
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint64_t dk_k = make_smem_desc_sw128(smem_u32(sK), 16, 1024);     // K as the K-major A operand of S^T
+      const uint64_t dv_k = make_smem_desc_sw128(smem_u32(sV), 16, 1024);     // V as the K-major A operand of dP^T
+      const uint64_t dk_mn = make_smem_desc_sw128(smem_u32(sK), 8192, 1024);  // K as the MN-major B operand of dQ
+      const uint64_t dq_k0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t do_k0 = make_smem_desc_sw128(smem_u32(sdO), 16, 1024);
+      const uint64_t dq_mn0 = make_smem_desc_sw128(smem_u32(sQ), 8192, 1024);
+      const uint64_t do_mn0 = make_smem_desc_sw128(smem_u32(sdO), 8192, 1024);
       auto issue_x = [&](int t, int hf) {
-        const int s = t & 1;
-        const uint32_t q_addr = smem_u32(sQ + s * AB_TILE) + hf * 8192, do_addr = smem_u32(sdO + s * AB_TILE) + hf * 8192;
+        const uint64_t off = static_cast<uint64_t>(((t % AB_QSTAGES) * AB_TILE + hf * 8192) >> 4);
         const uint32_t reg = tmem_base + hf * 128;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AB_DH / 16; ++k)
-          umma_bf16(reg, make_smem_desc_sw128(k_addr + k * 32, 16, 1024), make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                    id_x, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < AB_DH / 16; ++k)
-          umma_bf16(reg + 64, make_smem_desc_sw128(v_addr + k * 32, 16, 1024),
-                    make_smem_desc_sw128(do_addr + k * 32, 16, 1024), id_x, k > 0 ? 1u : 0u);
-        umma_commit(&x_full[hf]);
+          for (int k = 0; k < AB_DH / 16; ++k) {
+            umma_bf16(reg, dk_k + k * 2, dq_k0 + off + k * 2, id_x, k > 0 ? 1u : 0u);
+            umma_bf16(reg + 64, dv_k + k * 2, do_k0 + off + k * 2, id_x, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&x_full[hf]);
+        }
+        __syncwarp();
       };
-      auto issue_y = [&](int t, int hf) {
-        const int s = t & 1;
-        const uint32_t q_addr = smem_u32(sQ + s * AB_TILE) + hf * 8192, do_addr = smem_u32(sdO + s * AB_TILE) + hf * 8192;
-        const uint32_t reg = tmem_base + hf * 128;
-        // contraction over the 64 queries of this half: 4 steps of 16 query rows (2 KB of the MN-major B tile)
+      auto issue_y = [&](int t, int hf, bool last_of_tile) {
+        const uint64_t off = static_cast<uint64_t>(((t % AB_QSTAGES) * AB_TILE + hf * 8192) >> 4);
+        const uint32_t acc = (t > 0 || hf > 0) ? 1u : 0u;
+        if (elect_one()) {
+          // contraction over the 64 queries of this half: 4 steps of 16 query rows (2 KB of the MN-major B tile)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ts(tdV, reg + k * 8, make_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), id_y,
-                       (t > 0 || hf > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ts(tdK, reg + 64 + k * 8, make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), id_y,
-                       (t > 0 || hf > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_ts(tdV, tP + k * 8, do_mn0 + off + k * 128, id_y, k > 0 ? 1u : acc);
+            umma_bf16_ts(tdK, tP + 32 + k * 8, dq_mn0 + off + k * 128, id_y, k > 0 ? 1u : acc);
+          }
+          umma_commit(y_done);
+          if (last_of_tile) umma_commit(&qdo_empty[t % AB_QSTAGES]);  // Q / dO of this tile are no longer read
+        }
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
+      if (lane == 0) TRG(1);
       mbar_wait(&qdo_full[0], 0);
+      if (lane == 0) TRG(2);
       tc_fence_after();
       issue_x(0, 0);
       issue_x(0, 1);
       for (int t = 0; t < n_iter; ++t) {
         const uint32_t ph = t & 1;
-        mbar_wait(&c_done[0], ph);
-        tc_fence_after();
-        issue_y(t, 0);
-        if (t + 1 < n_iter) {
-          mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+        const bool more = t + 1 < n_iter;
+        if (lane == 0) TR(2, t, 0);
+        if (more) {
+          mbar_wait(&qdo_full[(t + 1) % AB_QSTAGES], ((t + 1) / AB_QSTAGES) & 1);
+          mbar_wait(&x_free[0], ph);  // S^T_0 / dP^T_0 of tile t are in registers: overwrite them right away
           tc_fence_after();
           issue_x(t + 1, 0);
         }
-        mbar_wait(&c_done[1], ph);
+        if (lane == 0) TR(2, t, 1);
+        mbar_wait(&c_done[0], ph);
+        if (lane == 0) TR(2, t, 2);
         tc_fence_after();
-        issue_y(t, 1);
-        umma_commit(&qdo_empty[t & 1]);  // Q / dO of this tile are no longer read once these retire
-        mbar_wait(&dq_free[t & 1], ((t >> 1) & 1) ^ 1);
-        tc_fence_after();
-        {  // dQ = dS K: contraction over the 128 keys (8 steps of 16 key rows)
-          const uint32_t ds_addr = smem_u32(sdS + (t & 1) * AB_DS);
-#pragma unroll
-          for (int k = 0; k < AB_T / 16; ++k)
-            umma_bf16(tdQ + (t & 1) * 64, make_smem_desc_sw128(ds_addr + k * 2048, AB_DS / 2, 1024),
-                      make_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), id_z, k > 0 ? 1u : 0u);
-          umma_commit(&z_full[t & 1]);
+        issue_y(t, 0, false);
+        if (lane == 0) TR(2, t, 3);
+        if (more) {
+          mbar_wait(&x_free[1], ph);
+          tc_fence_after();
+          issue_x(t + 1, 1);
         }
-        if (t + 1 < n_iter) issue_x(t + 1, 1);
+        if (lane == 0) TR(2, t, 4);
+        mbar_wait(&c_done[1], ph);
+        if (lane == 0) TR(2, t, 5);
+        tc_fence_after();
+        issue_y(t, 1, true);
+        if (t > 0) {
+          mbar_wait(dq_free, (t - 1) & 1);
+          tc_fence_after();
+        }
+        if (lane == 0) TR(2, t, 6);
+        {  // dQ = dS K: contraction over the 128 keys (8 steps of 16 key rows); the two 64-query halves of dS
+           // live in separate buffers: half 0 at buffer (t & 1), half 1 behind both (always a positive offset)
+          const uint64_t dds = make_smem_desc_sw128(smem_u32(sdS) + (t & 1) * (AB_DS / 2), (2 - (t & 1)) * (AB_DS / 2), 1024);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < AB_T / 16; ++k) umma_bf16(tdQ, dds + k * 128, dk_mn + k * 128, id_z, k > 0 ? 1u : 0u);
+            umma_commit(&z_full[t & 1]);
+          }
+          __syncwarp();
+        }
+        if (lane == 0) TR(2, t, 7);
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ===================== compute warpgroups: thread = key row, warpgroup = query half =====================
     const int hf = warp >> 2;             // which 64-query half of every tile
     const int r = (warp & 3) * 32 + lane;  // key row = TMEM lane
@@ -207,28 +286,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         mygrp = a.keygrp[kj];
       }
     }
+    const bool dead = has_dead && !live;
+    const long long sbase = (static_cast<long long>(b) * a.H + h) * a.N;
+    // raw per-query values of tile t go global -> shared with cp.async (no registers held across an iteration)
+    auto stage_async = [&](int t) {
+      if (wt < 64 && t < n_iter) {
+        const int qi = min(s_qt[t].x + hf * 64 + wt, a.N - 1);
+        cp_async4(&s_lse[hf][t & 1][wt], a.lse + sbase + qi);
+        cp_async4(&s_dl[hf][t & 1][wt], a.delta + sbase + qi);
+        cp_async4(&s_rb[hf][t & 1][wt], a.rowbits + qi);
+      }
+      cp_async_commit();
+    };
+    auto drain_dq = [&](int tp) {  // dQ of tile tp: TMEM -> registers -> fp32 swizzled smem (the reduce warp ships it)
+      mbar_wait(&z_full[tp & 1], (tp >> 1) & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tdQ + lane_sel, v0);
+      tmem_ld32(tdQ + lane_sel + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_free);
+      if (tp > 0) mbar_wait(sdq_free, (tp - 1) & 1);
+      uint8_t* rowp = sdQ + r * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) << 4)) = make_uint4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
+        *reinterpret_cast<uint4*>(rowp + AB_DQ / 2 + ((q ^ (r & 7)) << 4)) = make_uint4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(sdq_full);
+    };
+    stage_async(0);
     for (int t = 0; t < n_iter; ++t) {
       const uint32_t ph = t & 1;
-      const mca_attn_ref ref = a.qt_list[KT.kt_off + t];
-      const mca_attn_tile Q = a.q_tiles[ref.tile];
-      float* my_lse = s_lse + (hf * 2 + (t & 1)) * 64;
-      float* my_dl = s_dl + (hf * 2 + (t & 1)) * 64;
-      uint32_t* my_rb = s_rb + (hf * 2 + (t & 1)) * 64;
-      if (wt < 64) {  // stage this half's per-query lse (with the group mask folded in), delta and row bits
+      if (wt == 0) TR(hf, t, 0);
+      cp_async_wait_all();
+      if (wt < 64) {  // fix up the staged values in place: fold the group mask into lse, pre-negate for the FMAs
         const int qr = hf * 64 + wt;
-        const int qi = Q.start + qr;
-        float l2 = CUDART_INF_F, dl = 0.f;
-        uint32_t rb = 0;
-        if (qr < Q.len) {
-          const long long sidx = (static_cast<long long>(b) * a.H + h) * a.N + qi;
-          rb = a.rowbits[qi];
-          if (kgrp == 255 || ((rb >> kgrp) & 1u)) l2 = a.lse[sidx] * AB_LOG2E;
-          dl = a.delta[sidx];
-        }
-        my_lse[wt] = l2, my_dl[wt] = dl, my_rb[wt] = rb;
+        const bool valid = qr < s_qt[t].y;
+        const uint32_t rb = valid ? s_rb[hf][t & 1][wt] : 0u;
+        const bool sees = valid && (kgrp == 255 || ((rb >> kgrp) & 1u));
+        s_lse[hf][t & 1][wt] = sees ? -s_lse[hf][t & 1][wt] * AB_LOG2E : -CUDART_INF_F;
+        s_dl[hf][t & 1][wt] = valid ? -s_dl[hf][t & 1][wt] : 0.f;
+        s_rb[hf][t & 1][wt] = rb;
       }
       ab_bar_sync(1 + hf, 128);
+      stage_async(t + 1);  // after the barrier: every thread is done with the other buffer (tile t-1)
+      if (wt == 0) TR(hf, t, 1);
       mbar_wait(&x_full[hf], ph);
+      if (wt == 0) TR(hf, t, 2);
       tc_fence_after();
       uint32_t sv[2][32], dv[2][32];
       tmem_ld32(reg, sv[0]);
@@ -236,104 +343,84 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tmem_ld32(reg + 64, dv[0]);
       tmem_ld32(reg + 96, dv[1]);
       tmem_ld_wait();
-      if (t >= 2) mbar_wait(&z_full[t & 1], ((t - 2) >> 1) & 1);  // dS buffer (t&1) has been consumed by dQ(t-2)
-      uint8_t* ds_row = sdS + (t & 1) * AB_DS + hf * (AB_DS / 2) + r * 128;
+      if (wt == 0) TR(hf, t, 3);
+      tc_fence_before();
+      mbar_arrive(&x_free[hf]);  // the next tile's S^T / dP^T of this half may be issued now
+      const float4* lse4 = reinterpret_cast<const float4*>(s_lse[hf][t & 1]);
+      const float4* dl4 = reinterpret_cast<const float4*>(s_dl[hf][t & 1]);
+      const uint32_t* rbq = s_rb[hf][t & 1];
+      // P^T = exp2(S^T*log2e - lse2[q]),  dS^T = P^T * (dP^T - delta[q])   (in place in sv / dv)
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        const float4 l4 = lse4[g], d4 = dl4[g];
+        const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = g * 4 + i;
+          const float pi = fast_ex2(fmaf(__uint_as_float(sv[e >> 5][e & 31]), AB_LOG2E, lq[i]));
+          const float di = pi * (__uint_as_float(dv[e >> 5][e & 31]) + dq[i]);
+          sv[e >> 5][e & 31] = __float_as_uint(pi);
+          dv[e >> 5][e & 31] = __float_as_uint(di);
+        }
+      }
+      if (kgrp == 255) {  // mixed key groups (fusion sub-blocks): per-(query, key) visibility
+#pragma unroll
+        for (int e = 0; e < 64; ++e)
+          if (!((rbq[e] >> mygrp) & 1u)) sv[e >> 5][e & 31] = 0u, dv[e >> 5][e & 31] = 0u;
+      }
+      if (dead) {
+#pragma unroll
+        for (int e = 0; e < 64; ++e) sv[e >> 5][e & 31] = 0u, dv[e >> 5][e & 31] = 0u;
+      }
       uint32_t pp[32], dd[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 queries per step
-        float p[8], ds[8];
-#pragma unroll
-        for (int g4 = 0; g4 < 2; ++g4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(my_lse + c * 8 + g4 * 4);
-          const float4 d4 = *reinterpret_cast<const float4*>(my_dl + c * 8 + g4 * 4);
-          const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int e = c * 8 + g4 * 4 + i;
-            float pi = fast_ex2(fmaf(__uint_as_float(sv[e >> 5][e & 31]), AB_LOG2E, -lq[i]));
-            if (kgrp == 255 && !((my_rb[e] >> mygrp) & 1u)) pi = 0.f;
-            p[g4 * 4 + i] = pi;
-            ds[g4 * 4 + i] = pi * (__uint_as_float(dv[e >> 5][e & 31]) - dq[i]);
-          }
-        }
-        if (has_dead && !live) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) p[i] = 0.f, ds[i] = 0.f;
-        }
-        uint4 w;
-        w.x = pack_bf16x2(ds[0], ds[1]), w.y = pack_bf16x2(ds[2], ds[3]);
-        w.z = pack_bf16x2(ds[4], ds[5]), w.w = pack_bf16x2(ds[6], ds[7]);
-        dd[4 * c] = w.x, dd[4 * c + 1] = w.y, dd[4 * c + 2] = w.z, dd[4 * c + 3] = w.w;
-        pp[4 * c] = pack_bf16x2(p[0], p[1]), pp[4 * c + 1] = pack_bf16x2(p[2], p[3]);
-        pp[4 * c + 2] = pack_bf16x2(p[4], p[5]), pp[4 * c + 3] = pack_bf16x2(p[6], p[7]);
-        *reinterpret_cast<uint4*>(ds_row + ((c ^ (r & 7)) << 4)) = w;
+      for (int j = 0; j < 32; ++j) {
+        const int e = 2 * j;
+        pp[j] = pack_bf16x2(__uint_as_float(sv[e >> 5][e & 31]), __uint_as_float(sv[(e + 1) >> 5][(e + 1) & 31]));
+        dd[j] = pack_bf16x2(__uint_as_float(dv[e >> 5][e & 31]), __uint_as_float(dv[(e + 1) >> 5][(e + 1) & 31]));
       }
-      tmem_st32(reg, pp);        // P^T_h over the first 32 columns of S^T_h
-      tmem_st32(reg + 64, dd);   // dS^T_h over the first 32 columns of dP^T_h
+      if (wt == 0) TR(hf, t, 8);
+      // dS^T -> shared memory for the dQ product.  Half 0 is double buffered by tile parity; half 1 has one buffer
+      // that dQ(t-1) must have finished reading.
+      uint8_t* ds_row;
+      if (hf == 0) {
+        if (t >= 2) mbar_wait(&z_full[t & 1], ((t - 2) >> 1) & 1);
+        ds_row = sdS + (t & 1) * (AB_DS / 2) + r * 128;
+      } else {
+        if (t >= 1) mbar_wait(&z_full[(t - 1) & 1], ((t - 1) >> 1) & 1);
+        ds_row = sdS + 2 * (AB_DS / 2) + r * 128;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(ds_row + ((c ^ (r & 7)) << 4)) = make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
+      // the P^T / dS^T columns are shared by both halves: wait until the previous half's dV / dK products retired
+      const int yk = 2 * t + hf - 1;  // index of that commit on y_done
+      if (wt == 0) TR(hf, t, 4);
+      if (yk >= 0) {
+        mbar_wait(y_done, yk & 1);
+        tc_fence_after();
+      }
+      if (wt == 0) TR(hf, t, 5);
+      tmem_st32(tP + lane_sel, pp);
+      tmem_st32(tP + 32 + lane_sel, dd);
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&c_done[hf]);
-      // ---- warpgroup 1 drains dQ of the previous tile: TMEM -> fp32 swizzled smem -> TMA reduce-add
-      if (hf == 1 && t > 0) {
-        const int tp = t - 1;
-        const mca_attn_tile Qp = a.q_tiles[a.qt_list[KT.kt_off + tp].tile];
-        mbar_wait(&z_full[tp & 1], (tp >> 1) & 1);
-        tc_fence_after();
-        if (wt == 0) bulk_wait_group_read0();  // the previous reduce has finished reading sdQ
-        ab_bar_sync(2, 128);
-#pragma unroll
-        for (int cc = 0; cc < AB_DH / 32; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(tdQ + (tp & 1) * 64 + lane_sel + cc * 32, v);
-          tmem_ld_wait();
-          uint8_t* rowp = sdQ + cc * (AB_DQ / 2) + r * 128;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        tc_fence_before();
-        mbar_arrive(&dq_free[tp & 1]);
-        fence_proxy_async_smem();
-        ab_bar_sync(2, 128);
-        if (wt == 0) {
-          const int qrow = static_cast<int>(row0 + Qp.start);
-          tma_reduce_add_2d(&tm_dq, sdQ, h * AB_DH, qrow);
-          tma_reduce_add_2d(&tm_dq, sdQ + AB_DQ / 2, h * AB_DH + 32, qrow);
-          bulk_commit_group();
-        }
-      }
+      if (wt == 0) TR(hf, t, 6);
+      // the two warpgroups take turns draining dQ: tile tp is handled by warpgroup tp & 1 one iteration later
+      if (t > 0 && ((t - 1) & 1) == hf) drain_dq(t - 1);
+      if (wt == 0) TR(hf, t, 7);
     }
     if (n_iter > 0) {
       const int tp = n_iter - 1;
+      if ((tp & 1) == hf) drain_dq(tp);
       mbar_wait(&z_full[tp & 1], (tp >> 1) & 1);  // the last dQ product retired => every MMA of this CTA retired
       tc_fence_after();
-      if (hf == 1) {
-        const mca_attn_tile Qp = a.q_tiles[a.qt_list[KT.kt_off + tp].tile];
-        if (wt == 0) bulk_wait_group_read0();
-        ab_bar_sync(2, 128);
-#pragma unroll
-        for (int cc = 0; cc < AB_DH / 32; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(tdQ + (tp & 1) * 64 + lane_sel + cc * 32, v);
-          tmem_ld_wait();
-          uint8_t* rowp = sdQ + cc * (AB_DQ / 2) + r * 128;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        fence_proxy_async_smem();
-        ab_bar_sync(2, 128);
-        if (wt == 0) {
-          const int qrow = static_cast<int>(row0 + Qp.start);
-          tma_reduce_add_2d(&tm_dq, sdQ, h * AB_DH, qrow);
-          tma_reduce_add_2d(&tm_dq, sdQ + AB_DQ / 2, h * AB_DH + 32, qrow);
-          bulk_commit_group();
-        }
-      }
     }
     // ---- epilogue: warpgroup 0 writes dK, warpgroup 1 writes dV (+ the uniform-row correction); thread = key row.
     // tcgen05.ld is warp-collective: every lane loads, only rows inside the tile store.
+    if (wt == 0) TRG(3 + hf);
     {
       const bool store = r < KT.len;
       const int which = hf;  // 0: dK -> column block 1, 1: dV -> column block 2
@@ -369,10 +456,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
       }
     }
-    if (hf == 1 && wt == 0) bulk_wait_group0();
+    if (wt == 0) TRG(5 + hf);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TRG(7);
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -425,8 +513,7 @@ extern "C" int mca_attn_bwd(const void* qkv, const void* out, const void* dout, 
                             const mca_attn_tile* q_tiles, int n_qt, const uint32_t* rowbits, const uint8_t* keygrp,
                             const uint8_t* tile_grp, const uint8_t* padding, const uint8_t* kt_class, float* delta,
                             float* ucorr, float* dq_accum, void* dqkv, int B, int N, int H, void* stream_) {
-  (void)n_qt;
-  if (B <= 0 || N <= 0 || H * AB_DH != 512) return MCA_ERR_SHAPE;
+  if (B <= 0 || N <= 0 || H * AB_DH != 512 || n_qt <= 0 || n_qt > AB_MAX_ITERS) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int HD = H * AB_DH;
   const long long M = static_cast<long long>(B) * N;
@@ -455,3 +542,10 @@ extern "C" int mca_attn_bwd(const void* qkv, const void* out, const void* dout, 
   // dQ: fp32 accumulator -> bf16 first column block of dqkv
   return mca_cast_f32_bf16(dq_accum, HD, dqkv, 3 * HD, M, HD, stream_);
 }
+
+#ifdef MCA_TRACE
+extern "C" int mca_debug_read_trace(long long* host_dst, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_dst, mca::g_trace, sizeof(long long) * n) == cudaSuccess ? 0 : 3;
+}
+#endif

@@ -97,66 +97,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a)
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
 
   if (warp == 4) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_expect_tx(q_full, AT_TILE_BYTES);
       tma_load_2d(sQ, &tm_qkv, q_full, h * AT_DH, static_cast<int>(row0 + Q.start));
-      int it = 0;
-      for (int t = 0; t < Q.kt_cnt; ++t) {
-        const mca_attn_ref ref = a.kt_list[Q.kt_off + t];
-        if (cls[ref.tile] == 2) continue;
-        const int krow = static_cast<int>(row0 + a.k_tiles[ref.tile].start);
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int t = 0; t < Q.kt_cnt; ++t) {
+      const mca_attn_ref ref = a.kt_list[Q.kt_off + t];
+      if (cls[ref.tile] == 2) continue;
+      const int krow = static_cast<int>(row0 + a.k_tiles[ref.tile].start);
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&k_full[st], AT_TILE_BYTES);
         tma_load_2d(sK + st * AT_TILE_BYTES, &tm_qkv, &k_full[st], a.H * AT_DH + h * AT_DH, krow);
-        mbar_wait(&v_empty[st], ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[st], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&v_full[st], AT_TILE_BYTES);
         tma_load_2d(sV + st * AT_TILE_BYTES, &tm_qkv, &v_full[st], 2 * a.H * AT_DH + h * AT_DH, krow);
-        ++it;
       }
+      __syncwarp();
+      ++it;
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, false, false);
-      constexpr uint32_t idesc_o = make_idesc_bf16(AT_BM, AT_DH, false, true);
-      const uint32_t q_addr = smem_u32(sQ);
-      auto issue_pv = [&](int j) {
-        const int st = j & 1;
-        const uint32_t v_addr = smem_u32(sV + st * AT_TILE_BYTES);
-        mbar_wait(&v_full[st], (j >> 1) & 1);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
+    // The whole warp runs the loop and the waits (convergent code keeps the descriptors in uniform registers, so a
+    // tcgen05.mma costs one uniform add); one elected lane issues the MMAs and commits.
+    constexpr uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, false, false);
+    constexpr uint32_t idesc_o = make_idesc_bf16(AT_BM, AT_DH, false, true);
+    const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+    auto issue_pv = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      const uint64_t dv = dv0 + static_cast<uint64_t>((st * AT_TILE_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k)
-          umma_bf16_ts(tO, tP + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o,
-                       (j > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_ts(tO, tP + k * 8, dv + k * (2048 >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
-      };
-      mbar_wait(q_full, 0);
-      int it = 0;
-      for (int t = 0; t < Q.kt_cnt; ++t) {
-        const mca_attn_ref ref = a.kt_list[Q.kt_off + t];
-        if (cls[ref.tile] == 2) continue;
-        const int st = it & 1;
-        const uint32_t k_addr = smem_u32(sK + st * AT_TILE_BYTES);
-        mbar_wait(&k_full[st], (it >> 1) & 1);
-        mbar_wait(s_empty, (it & 1) ^ 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    int it = 0;
+    for (int t = 0; t < Q.kt_cnt; ++t) {
+      const mca_attn_ref ref = a.kt_list[Q.kt_off + t];
+      if (cls[ref.tile] == 2) continue;
+      const int st = it & 1;
+      mbar_wait(&k_full[st], (it >> 1) & 1);
+      mbar_wait(s_empty, (it & 1) ^ 1);
+      tc_fence_after();
+      const uint64_t dk = dk0 + static_cast<uint64_t>((st * AT_TILE_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_DH / 16; ++k)
-          umma_bf16(tS, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
-                    idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < AT_DH / 16; ++k) umma_bf16(tS, dq0 + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&k_empty[st]);
         umma_commit(s_full);
-        if (it > 0) issue_pv(it - 1);
-        ++it;
       }
+      __syncwarp();
       if (it > 0) issue_pv(it - 1);
+      ++it;
     }
+    if (it > 0) issue_pv(it - 1);
   } else {
     // ===================== softmax / epilogue: thread = query row =====================
     const int r = warp * 32 + lane;

@@ -104,22 +104,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % tiles_n;
-        const int mt = (tile / tiles_n) % tiles_m;
-        const int z = tile / (tiles_n * tiles_m);
-        const int m0 = mt * BM, n0 = nt * BN;
-        const int kb0 = z * kb_per_split;
-        const int kb1 = min(kb_total, kb0 + kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % tiles_n;
+      const int mt = (tile / tiles_n) % tiles_m;
+      const int z = tile / (tiles_n * tiles_m);
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int kb0 = z * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = sA + s * A_BYTES;
+        uint8_t* b_dst = sB + s * B_BYTES;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-          uint8_t* a_dst = sA + s * A_BYTES;
-          uint8_t* b_dst = sB + s * B_BYTES;
           if constexpr (!A_MN) {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
           } else {
@@ -132,44 +132,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int h = 0; h < BN / 64; ++h) tma_load_2d(b_dst + h * 8192, &tmB, &full_bar[s], n0 + 64 * h, kb * BK);
           }
-          if (++s == STAGES) s = 0, ph ^= 1;
         }
+        __syncwarp();
+        if (++s == STAGES) s = 0, ph ^= 1;
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int z = tile / (tiles_n * tiles_m);
-        const int kb0 = z * kb_per_split;
-        const int kb1 = min(kb_total, kb0 + kb_per_split);
-        mbar_wait(&tempty_bar[as], aph ^ 1);
+    // ===================== MMA issuer =====================
+    // The whole warp runs the loop (convergent code keeps the shared-memory descriptors in uniform registers, so
+    // one tcgen05.mma costs a couple of uniform adds); a single elected lane issues the MMAs and the commits.
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    // k-step inside a 64-wide k-block: K-major advances 32 B along the swizzled row, MN-major 16 k-rows = 2 KB
+    constexpr uint64_t a_step = (A_MN ? 2048u : 32u) >> 4, b_step = (B_MN ? 2048u : 32u) >> 4;
+    const uint64_t da0 = A_MN ? make_smem_desc_sw128(smem_u32(sA), 8192, 1024) : make_smem_desc_sw128(smem_u32(sA), 16, 1024);
+    const uint64_t db0 = B_MN ? make_smem_desc_sw128(smem_u32(sB), 8192, 1024) : make_smem_desc_sw128(smem_u32(sB), 16, 1024);
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int z = tile / (tiles_n * tiles_m);
+      const int kb0 = z * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+        const uint64_t da = da0 + static_cast<uint64_t>((s * A_BYTES) >> 4);
+        const uint64_t db = db0 + static_cast<uint64_t>((s * B_BYTES) >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: 16 bf16 = 32 B along the swizzled row; rows of 8 are 1024 B apart (SBO).
-            // MN-major: 16 k-rows = 2 KB; the next 64 MN elements live one TMA box (8 KB) further (LBO).
-            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, da + k * a_step, db + k * b_step, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
-          if (++s == STAGES) s = 0, ph ^= 1;
+          if (kb + 1 == kb1) umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
-        if (++as == 2) as = 0, aph ^= 1;
+        __syncwarp();
+        if (++s == STAGES) s = 0, ph ^= 1;
       }
+      if (++as == 2) as = 0, aph ^= 1;
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps: TMEM -> registers -> swizzled smem -> TMA store =====================
@@ -188,9 +189,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nt * BN;
       const int row0 = mt * BM + q * 32;
       // the previous tile's TMA stores must have finished reading this warp's staging area
-      if (lane == 0) bulk_wait_group_read0();
+      if (elect_one()) bulk_wait_group_read0();  // same membermask -> same leader as the lane that issued the stores
       __syncwarp();
-      if (has_aux && lane == 0) {
+      if (has_aux && elect_one()) {
         mbar_expect_tx(xbar, 8192);
         if (p.mode == MCA_EPI_RESID) {  // fp32 boxes [32 cols x 32 rows]
           tma_load_2d(stg, &tmAux, xbar, n0 + hf * 64, row0);
@@ -234,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_2d(&tmO0, stg, ncol, row0);
           bulk_commit_group();
         }
@@ -266,7 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_3d(&tmO0, stg, n0 + hf * 64, row0, z);
           tma_store_3d(&tmO0, stg + 4096, n0 + hf * 64 + 32, row0, z);
           bulk_commit_group();
@@ -294,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_2d(&tmO1, stg, n0 + hf * 32, row0);
           tma_store_2d(&tmO1, stg + 2048, n0 + 64 + hf * 32, row0);
           tma_store_2d(&tmO0, stg + 4096, (n0 / 128) * 64 + hf * 32, row0);
@@ -322,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           const int blk = (n0 + hf * 64) / 64;
           tma_store_2d(&tmO0, stg, blk * 128, row0);
           tma_store_2d(&tmO0, stg + 4096, blk * 128 + 64, row0);
@@ -330,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if (lane == 0) bulk_wait_group0();
+    if (elect_one()) bulk_wait_group0();
   }
 
   tc_fence_before();
