@@ -160,10 +160,11 @@ int mca_pool_attn_fwd(const float* qp, const void* kv, const uint8_t* padding, c
 int mca_pool_attn_bwd(const float* dout, const float* qp, const void* kv, const float* probs,
                       const uint8_t* full_masked, float* ds_scratch, void* dkv, float* dqp, int B, int H, int R, int N,
                       void* stream);
-/* tiny fp32 GEMM with arbitrary strides: C[m,n] = alpha*sum_k A(m,k)B(n,k) (+C) (+add) — return-token projections */
+/* small fp32 GEMM with arbitrary strides: C[m,n] = alpha*sum_k A(m,k)B(n,k) (+C) (+add[m % add_rows, n]; add_rows = 0:
+ * add[m, n]) — the return-token projections around attention pooling (model.py:472-473, R*B <= 128 rows) */
 int mca_small_gemm_f32(const float* A, long long sam, long long sak, const float* Bm, long long sbn, long long sbk,
-                       float* C, long long ldc, const float* add, long long ldadd, int M, int N, int K, float alpha,
-                       int accumulate, void* stream);
+                       float* C, long long ldc, const float* add, long long ldadd, int add_rows, int M, int N, int K,
+                       float alpha, int accumulate, void* stream);
 
 /* All-pairs temperature-scaled InfoNCE (model.py:196-232 + utils/contrastive_loss_with_temperature.py:71-100,187).
  * pooled_all: [GB, R, d] all-gathered pooled tokens, local rows at rank*B; losses[n_pairs] (NaN = no selected row);

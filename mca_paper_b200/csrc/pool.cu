@@ -216,30 +216,48 @@ pool_bwd_kv_kernel(const float* __restrict__ ds, const float* __restrict__ probs
   reinterpret_cast<uint4*>(ov)[0] = q0, reinterpret_cast<uint4*>(ov)[1] = q1;
 }
 
-// ---- tiny fp32 GEMM: C[m,n] = alpha * sum_k A(m,k) B(n,k) (+ C if accumulate) (+ add[m,n]); arbitrary strides
+// ---- small fp32 GEMM: C[m,n] = alpha * sum_k A(m,k) B(n,k) (+ C if accumulate) (+ add[m % add_rows, n]); arbitrary
+// strides.  32x32 output tile per block (these problems have at most a few hundred rows: small tiles keep every SM
+// busy), 2x2 outputs per thread, 32-wide k steps staged through shared memory.
 __global__ void __launch_bounds__(256)
 small_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm,
                   long long sbn, long long sbk, float* __restrict__ C, long long ldc, const float* __restrict__ add,
-                  long long ldadd, int M, int N, int K, float alpha, int accumulate) {
-  __shared__ float As[16][17], Bs[16][17];
+                  long long ldadd, int add_rows, int M, int N, int K, float alpha, int accumulate) {
+  __shared__ float As[32][33], Bs[32][33];  // [k][row]
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
-  float acc = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    const int am = blockIdx.y * 16 + ty, ak = k0 + tx;
-    As[ty][tx] = (am < M && ak < K) ? A[am * sam + ak * sak] : 0.f;
-    const int bn = blockIdx.x * 16 + ty, bk = k0 + tx;
-    Bs[ty][tx] = (bn < N && bk < K) ? Bm[bn * sbn + bk * sbk] : 0.f;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    // element e -> (row = e / 32, k = e % 32) when k is the fast stride, otherwise (k = e / 32, row = e % 32), so the
+    // global reads stay coalesced for either layout
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      int ra, ka, rb, kb;
+      if (sak == 1) ra = e / 32, ka = e % 32; else ka = e / 32, ra = e % 32;
+      if (sbk == 1) rb = e / 32, kb = e % 32; else kb = e / 32, rb = e % 32;
+      As[ka][ra] = (m0 + ra < M && k0 + ka < K) ? A[(m0 + ra) * sam + (k0 + ka) * sak] : 0.f;
+      Bs[kb][rb] = (n0 + rb < N && k0 + kb < K) ? Bm[(n0 + rb) * sbn + (k0 + kb) * sbk] : 0.f;
+    }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc += As[ty][k] * Bs[tx][k];
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1], b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+      acc[0][0] += a0 * b0, acc[0][1] += a0 * b1, acc[1][0] += a1 * b0, acc[1][1] += a1 * b1;
+    }
     __syncthreads();
   }
-  if (m < M && n < N) {
-    float v = alpha * acc;
-    if (accumulate) v += C[m * ldc + n];
-    if (add != nullptr) v += add[m * ldadd + n];
-    C[m * ldc + n] = v;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + tx * 2 + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      if (accumulate) v += C[m * ldc + n];
+      if (add != nullptr) v += add[(add_rows > 0 ? m % add_rows : m) * ldadd + n];
+      C[m * ldc + n] = v;
+    }
   }
 }
 
@@ -285,11 +303,11 @@ extern "C" int mca_pool_attn_bwd(const float* dout, const float* qp, const void*
 }
 
 extern "C" int mca_small_gemm_f32(const float* A, long long sam, long long sak, const float* Bm, long long sbn,
-                                  long long sbk, float* C, long long ldc, const float* add, long long ldadd, int M,
-                                  int N, int K, float alpha, int accumulate, void* stream) {
+                                  long long sbk, float* C, long long ldc, const float* add, long long ldadd,
+                                  int add_rows, int M, int N, int K, float alpha, int accumulate, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return MCA_ERR_SHAPE;
-  dim3 grid((N + 15) / 16, (M + 15) / 16);
+  dim3 grid((N + 31) / 32, (M + 31) / 32);
   small_gemm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, add,
-                                                                             ldadd, M, N, K, alpha, accumulate);
+                                                                             ldadd, add_rows, M, N, K, alpha, accumulate);
   return check_launch();
 }

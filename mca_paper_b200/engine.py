@@ -345,8 +345,8 @@ class Engine:
         call("mca_pool_attn_fwd", P(ws["qp"]), P(ws["kvp"]), P(ws["padding"]), P(self.keygrp), P(self.pool_rowbits),
              P(ws["probs"]), P(ws["fm"]), P(ws["po"]), self.B, self.H, self.R, self.N, S())
         # pooled[b, r] = po[b, r] Wo^T + return_tokens[r]
-        for b in range(self.B):
-            ops.small_gemm(ws["po"][b], D, 1, wo, D, 1, ws["pooled"][b], D, self.R, D, D, add=rt, ldadd=D)
+        ops.small_gemm(ws["po"].view(self.B * self.R, D), D, 1, wo, D, 1, ws["pooled"].view(self.B * self.R, D), D,
+                       self.B * self.R, D, D, add=rt, ldadd=D, add_rows=self.R)
         return ws["pooled"]
 
     def loss_forward(self, pooled):

@@ -44,7 +44,7 @@ _SIGS = {
     "mca_attn_bwd": [VP, VP, VP, VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
     "mca_pool_attn_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
     "mca_pool_attn_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
-    "mca_small_gemm_f32": [VP, I64, I64, VP, I64, I64, VP, I64, VP, I64, I32, I32, I32, F32, I32, VP],
+    "mca_small_gemm_f32": [VP, I64, I64, VP, I64, I64, VP, I64, VP, I64, I32, I32, I32, I32, F32, I32, VP],
     "mca_contrastive_allpairs_fwd": [VP, VP, VP, I32, VP, I32, I32, I32, I32, I32, I32, F32, F32, VP, VP, VP, VP],
     "mca_contrastive_allpairs_bwd": [VP, VP, VP, I32, VP, I32, I32, I32, I32, I32, I32, VP, VP, VP, VP],
     "mca_clip_adamw_step": [VP, VP, VP, VP, I64, VP, VP, VP, F32, VP, VP],
@@ -83,10 +83,13 @@ KERNELS_PER_CALL = {"mca_build_offsets": 2, "mca_attn_fwd": 2, "mca_attn_bwd": 3
                     "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3}
 COUNT = {"n": 0}
 PROFILE = {"on": False, "events": []}
+RECORD = {"on": False, "calls": []}  # (name, tag, args) of every entry-point call, for isolated device timing
 
 
 def call(name: str, *args, tag: str = ""):
     COUNT["n"] += KERNELS_PER_CALL.get(name, 1)
+    if RECORD["on"]:
+        RECORD["calls"].append((name, tag, args))
     if PROFILE["on"]:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -126,6 +129,6 @@ def layernorm512_bwd(dy, x, stats, gamma, dx32, dx16, dgamma, dbeta, rows, pad=N
          int(seg_len), int(out_rows_per_b), int(out_row_off), int(rows), S())
 
 
-def small_gemm(A, sam, sak, Bm, sbn, sbk, Cm, ldc, M, N, K, alpha=1.0, accumulate=False, add=None, ldadd=0):
+def small_gemm(A, sam, sak, Bm, sbn, sbk, Cm, ldc, M, N, K, alpha=1.0, accumulate=False, add=None, ldadd=0, add_rows=0):
     call("mca_small_gemm_f32", P(A), int(sam), int(sak), P(Bm), int(sbn), int(sbk), P(Cm), int(ldc), P(add), int(ldadd),
-         int(M), int(N), int(K), float(alpha), int(bool(accumulate)), S())
+         int(add_rows), int(M), int(N), int(K), float(alpha), int(bool(accumulate)), S())
