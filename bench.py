@@ -256,11 +256,11 @@ def main():
     # consecutive launches touch different layers' buffers: > L2) between two CUDA events.  This removes the host
     # launch gaps that per-call events in an eager pass include.
     roof, per_kernel = None, None
+    ops.RECORD["on"], ops.RECORD["calls"] = True, []
+    trainer._run_eager()  # on every rank: the step contains the three collectives
+    torch.cuda.synchronize()
+    ops.RECORD["on"] = False
     if rank == 0:
-        ops.RECORD["on"], ops.RECORD["calls"] = True, []
-        trainer._run_eager()
-        torch.cuda.synchronize()
-        ops.RECORD["on"] = False
         calls = ops.RECORD["calls"]
         groups = {}
         for name, tag, a in calls:
@@ -354,6 +354,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
