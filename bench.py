@@ -231,18 +231,29 @@ def main():
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
-    # ---- timed region 2: end to end from host buffers (H2D of the batch + D2H of the loss every step)
+    # ---- timed region 2: end to end from host buffers.  Every step's batch is copied pinned-host -> device inside the
+    # timed region (on a copy stream, one step ahead of the compute) and every step's loss summary is read back to
+    # the host inside it (the read of step i completes while step i+1 runs).
+    loss_pin2 = [torch.empty(4, pin_memory=True) for _ in range(2)]
+    loss_evt = [torch.cuda.Event() for _ in range(2)]
+    trainer._ensure_pipeline()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
-        trainer.h2d()
-        summary = trainer.step_staged()
-        loss_pinned.copy_(summary, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    trainer.prefetch(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            trainer.prefetch((i + 1) & 1)
+        summary = trainer.step_from_slot(i & 1)
+        loss_pin2[i & 1].copy_(summary, non_blocking=True)
+        loss_evt[i & 1].record()
+        if i > 0:
+            loss_evt[(i - 1) & 1].synchronize()
+    loss_evt[(args.steps - 1) & 1].synchronize()
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    loss_pinned = loss_pin2[(args.steps - 1) & 1]
     clocks = sampler.stop() if sampler is not None else None
     final_loss = float(loss_pinned[0])
 

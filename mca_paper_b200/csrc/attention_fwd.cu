@@ -248,21 +248,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a)
       l_run *= alpha;
       m2 = m2n;
       const float moff = (m2 == -CUDART_INF_F) ? 0.f : m2;
-      float sum0 = 0.f, sum1 = 0.f;
+      uint64_t sum2 = f2_pack(0.f, 0.f);
+      const uint64_t log2e2 = f2_pack(LOG2E, LOG2E), nmoff2 = f2_pack(-moff, -moff);
 #pragma unroll
       for (int hh = 0; hh < 4; ++hh) {  // 32 keys -> 16 packed columns
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float p0 = fast_ex2(fmaf(__uint_as_float(sv[hh][2 * j]), LOG2E, -moff));
-          const float p1 = fast_ex2(fmaf(__uint_as_float(sv[hh][2 * j + 1]), LOG2E, -moff));
-          sum0 += p0;
-          sum1 += p1;
+          float t0, t1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[hh][2 * j]), __uint_as_float(sv[hh][2 * j + 1])), log2e2, nmoff2), t0, t1);
+          const float p0 = fast_ex2(t0), p1 = fast_ex2(t1);
+          sum2 = f2_add(sum2, f2_pack(p0, p1));
           pk[j] = pack_bf16x2(p0, p1);
         }
         tmem_st16(tP + lane_sel + hh * 16, pk);
       }
-      l_run += sum0 + sum1;
+      {
+        float sum0, sum1;
+        f2_unpack(sum2, sum0, sum1);
+        l_run += sum0 + sum1;
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);

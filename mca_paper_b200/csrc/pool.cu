@@ -108,6 +108,102 @@ pool_fwd_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ 
         part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
 }
 
+// Same computation with one block per (sample, head): K and V rows are read ONCE for all R pooled rows (the kernel
+// above re-reads them per row).  Scores / probabilities of the whole [N, R] block live in shared memory.
+// grid = B*H, block 512; requires R <= 16 and N * round_up(R,4) * 4 bytes of shared memory.
+__global__ void __launch_bounds__(512)
+pool_fwd_bh_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ kv, const uint8_t* __restrict__ padding,
+                   const uint8_t* __restrict__ keygrp, const uint32_t* __restrict__ rowbits, float* __restrict__ probs,
+                   uint8_t* __restrict__ full_masked, float* __restrict__ out, int B, int H, int R, int N, int RS) {
+  extern __shared__ float sm[];
+  float* q = sm;              // [16][64]
+  float* sc = sm + 16 * DH;   // [N][RS]
+  const int h = blockIdx.x % H, b = blockIdx.x / H;
+  const int ld = 2 * H * DH;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 16 * DH; i += blockDim.x) q[i] = (i / DH) < R ? qp[(i / DH) * H * DH + h * DH + (i % DH)] : 0.f;
+  __syncthreads();
+  // ---- phase 1: masked scores
+  for (int j = tid; j < N; j += blockDim.x) {
+    float k[DH];
+    load_row64(kv + (static_cast<long long>(b) * N + j) * ld + h * DH, k);
+    const bool pad = padding[static_cast<long long>(b) * N + j] != 0;
+    const uint32_t kg = keygrp[j];
+    for (int r = 0; r < R; ++r) {
+      const float4* q4 = reinterpret_cast<const float4*>(q + r * DH);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) {
+        const float4 w = q4[c];
+        s += w.x * k[4 * c] + w.y * k[4 * c + 1] + w.z * k[4 * c + 2] + w.w * k[4 * c + 3];
+      }
+      const bool ok = !pad && ((rowbits[r] >> kg) & 1u);
+      sc[j * RS + r] = ok ? s : -CUDART_INF_F;
+    }
+    for (int r = R; r < RS; ++r) sc[j * RS + r] = 0.f;
+  }
+  __syncthreads();
+  // ---- phase 2: softmax of row r by warp r (16 warps)
+  for (int r = warp; r < R; r += blockDim.x / 32) {
+    float mx = -CUDART_INF_F;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sc[j * RS + r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float* prow = probs + (static_cast<long long>(b * H + h) * R + r) * N;
+    if (mx == -CUDART_INF_F) {
+      // every key masked: softmax of a constant row = 1/N over all N keys (padded and disallowed ones included)
+      const float u = 1.0f / static_cast<float>(N);
+      for (int j = lane; j < N; j += 32) sc[j * RS + r] = u, prow[j] = u;
+      if (lane == 0 && h == 0) full_masked[b * R + r] = 1;
+    } else {
+      float se = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        const float s = sc[j * RS + r];
+        const float e = s == -CUDART_INF_F ? 0.f : expf(s - mx);
+        sc[j * RS + r] = e;
+        se += e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      const float inv = 1.0f / se;
+      for (int j = lane; j < N; j += 32) {
+        const float p = sc[j * RS + r] * inv;
+        sc[j * RS + r] = p;
+        prow[j] = p;
+      }
+      if (lane == 0 && h == 0) full_masked[b * R + r] = 0;
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: out[r, c] = sum_j p[r, j] * V[j, c]; thread = (dim c, key group g of 8)
+  const int c = tid % DH, g = tid / DH;
+  float acc[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+  for (int j = g; j < N; j += 8) {
+    const float v = __bfloat162float(kv[(static_cast<long long>(b) * N + j) * ld + H * DH + h * DH + c]);
+    const float4* pj = reinterpret_cast<const float4*>(sc + j * RS);
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4)
+      if (r4 * 4 < R) {  // rows beyond R inside the last group of four hold padding that is never written out
+        const float4 p4 = pj[r4];
+        acc[4 * r4] += p4.x * v, acc[4 * r4 + 1] += p4.y * v, acc[4 * r4 + 2] += p4.z * v, acc[4 * r4 + 3] += p4.w * v;
+      }
+  }
+  __syncthreads();  // everyone is done reading sc: reuse it for the cross-group reduction [8][16][64]
+  float* part = sc;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) part[(g * 16 + r) * DH + c] = acc[r];
+  __syncthreads();
+  for (int i = tid; i < R * DH; i += blockDim.x) {
+    const int r = i / DH, cc = i % DH;
+    float t = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) t += part[(gg * 16 + r) * DH + cc];
+    out[(static_cast<long long>(b) * R + r) * H * DH + h * DH + cc] = t;
+  }
+}
+
 // dS (written over `probs_to_ds` copy): grid = B*H*R.  dout [B, R, H*64] fp32.
 __global__ void __launch_bounds__(256)
 pool_bwd_scores_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ kv,
@@ -274,6 +370,18 @@ extern "C" int mca_pool_attn_fwd(const float* qp, const void* kv, const uint8_t*
     cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(pool_bwd_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
+  }
+  const int RS = (R + 3) / 4 * 4;
+  const size_t need = (16 * DH + static_cast<size_t>(N) * RS) * sizeof(float);
+  if (R <= 16 && need <= 200 * 1024 && static_cast<size_t>(N) * RS >= 8 * 16 * DH) {
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(pool_fwd_bh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr2 = true;
+    }
+    pool_fwd_bh_kernel<<<B * H, 512, need, reinterpret_cast<cudaStream_t>(stream)>>>(
+        qp, reinterpret_cast<const __nv_bfloat16*>(kv), padding, keygrp, rowbits, probs, full_masked, out, B, H, R, N, RS);
+    return check_launch();
   }
   pool_fwd_kernel<<<B * H * R, 256, N * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       qp, reinterpret_cast<const __nv_bfloat16*>(kv), padding, keygrp, rowbits, probs, full_masked, out, B, H, R, N);

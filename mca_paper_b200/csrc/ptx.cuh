@@ -224,6 +224,31 @@ __device__ __forceinline__ float fast_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 process two fp32 lanes per instruction)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // erf-GELU and its derivative from one exp and one reciprocal: erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7,
 // far below the bf16 rounding of every consumer).  cdf = Phi(x), pdf = phi(x):  gelu = x*cdf, gelu' = cdf + x*pdf.
 __device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {

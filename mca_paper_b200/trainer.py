@@ -67,6 +67,38 @@ class Trainer:
             for k, v in d.items():
                 self._dev_batch[m][k].copy_(v, non_blocking=True)
 
+    # ---- pipelined input path: the H2D copy of the next batch runs on a copy stream under the current step
+    def _ensure_pipeline(self):
+        if getattr(self, "_copy_stream", None) is not None:
+            return
+        self._copy_stream = torch.cuda.Stream()
+        self._slots = [{m: {k: torch.empty_like(v) for k, v in d.items()} for m, d in self._dev_batch.items()}
+                       for _ in range(2)]
+        self._ready = [torch.cuda.Event() for _ in range(2)]      # H2D into the slot finished
+        self._consumed = [torch.cuda.Event() for _ in range(2)]   # the step has copied the slot into its inputs
+        for e in self._consumed:
+            e.record()
+
+    def prefetch(self, slot: int):
+        """Start the H2D copy of the pinned batch into staging slot `slot` on the copy stream."""
+        self._ensure_pipeline()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed[slot])
+            for m, d in self._pinned.items():
+                for k, v in d.items():
+                    self._slots[slot][m][k].copy_(v, non_blocking=True)
+            self._ready[slot].record()
+
+    def step_from_slot(self, slot: int):
+        """Run one step on the batch prefetched into `slot` (device-to-device hand-over into the graph's inputs)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[slot])
+        for m, d in self._slots[slot].items():
+            for k, v in d.items():
+                self._dev_batch[m][k].copy_(v, non_blocking=True)
+        self._consumed[slot].record()
+        return self.step_staged()
+
     # ------------------------------------------------------------------------------------------ step pieces
     def _seg_forward(self):
         self._pooled = self.eng.trunk_forward(self._dev_batch)
