@@ -12,6 +12,8 @@
 // Warp roles (384 threads, one CTA per SM): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 4-11 epilogue.  Epilogue warp w owns TMEM lane quarter w%4 (32 accumulator rows) and column half (w-4)/4
 // (64 of the tile's 128 columns); it has a private 8 KB staging area, so the epilogue needs no block-wide barrier.
+#include <cstdlib>
+
 #include "mca_b200.h"
 #include "ptx.cuh"
 #include "runtime.h"
@@ -362,6 +364,21 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 using namespace mca;
 
+namespace mca {
+int gemm2_dispatch(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb, int M, int N,
+                   int K, int k_splits, int mode, void* out0, long long ld0, void* out1, long long ld1, const void* aux0,
+                   long long ldaux, const float* bias, float alpha, cudaStream_t stream);
+// CTA-pair kernel (gemm2.cu) unless MCA_GEMM_2CTA=0 or the problem has fewer than 256 rows
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCA_GEMM_2CTA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+}  // namespace mca
+
 extern "C" int mca_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
                              long long ldb, int M, int N, int K, int k_splits, int mode, void* out0, long long ld0,
                              void* out1, long long ld1, const void* aux0, long long ldaux, const float* bias,
@@ -375,6 +392,9 @@ extern "C" int mca_gemm_bf16(const void* A, int a_mn_major, long long lda, const
       (mode == MCA_EPI_GEGLU_BWD && (N % 64) != 0))
     return MCA_ERR_ARG;
   k_splits = gemm_effective_splits(K, k_splits);  // every split owns at least one k-block
+  if (M >= 256 && use_cta_pairs())
+    return gemm2_dispatch(A, a_mn_major, lda, B, b_mn_major, ldb, M, N, K, k_splits, mode, out0, ld0, out1, ld1, aux0, ldaux,
+                          bias, alpha, stream);
   CUtensorMap tmA, tmB, tmO0, tmO1, tmAux;
   int rc;
   // K-major: global [rows, K] (K contiguous), box {64 k, rows}.  MN-major: global [K, rows] (rows contiguous), box {64 rows, 64 k}.
