@@ -277,6 +277,7 @@ def main():
         for name, tag, a in calls:
             groups.setdefault(f"{name}:{tag}" if tag else name, []).append((name, a))
         replay_ok = ("mca_gemm_bf16", "mca_attn_fwd", "mca_attn_bwd", "mca_layernorm512_fwd", "mca_layernorm512_bwd",
+                     "mca_add_layernorm512_fwd", "mca_batchsum_rows", "mca_broadcast_rows", "mca_cast_f32_bf16",
                      "mca_pool_attn_fwd", "mca_pool_attn_bwd", "mca_small_gemm_f32", "mca_colsum", "mca_pack_weights",
                      "mca_unpack_grads", "mca_layernorm_in_fwd", "mca_layernorm_in_param_bwd", "mca_build_offsets")
         per_kernel = {}

@@ -105,9 +105,16 @@ int mca_build_offsets(const void* const* masks_host, const int* elem_sizes_host,
 int mca_layernorm512_fwd(const float* x, const float* gamma, const float* beta, float* y32, void* y16, float* stats,
                          const uint8_t* pad, const float* pe, int seg_len, int out_rows_per_b, int out_row_off,
                          long long rows, void* stream);
-int mca_layernorm512_bwd(const float* dy, const float* x, const float* stats, const float* gamma, float* dx32,
-                         void* dx16, float* dgamma, float* dbeta, const uint8_t* pad, int seg_len, int out_rows_per_b,
-                         int out_row_off, long long rows, void* stream);
+/* dy_delta_bf16 (optional, same row mapping as dy): gradient of the branch GEMM, added to dy before the backward */
+int mca_layernorm512_bwd(const float* dy, const void* dy_delta_bf16, const float* x, const float* stats,
+                         const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta, const uint8_t* pad,
+                         int seg_len, int out_rows_per_b, int out_row_off, long long rows, void* stream);
+/* Residual add fused with the next LayerNorm (model.py:118-122; quirk Q1: the residual is the NORMED tensor):
+ * xnew = LN(xprev; stats_prev, gamma_prev, beta_prev) + y  (fp32, optional), out = LN(xnew; gamma, beta) as the bf16
+ * operand of the next GEMM, stats = its (mean, rstd).  The normed residual is recomputed, never stored in fp32. */
+int mca_add_layernorm512_fwd(const float* xprev, const float* stats_prev, const float* gamma_prev,
+                             const float* beta_prev, const void* y_bf16, float* xnew, const float* gamma,
+                             const float* beta, void* out_bf16, float* stats, long long rows, void* stream);
 /* Input LayerNorm of EmbeddedSequenceEncoder (encoders.py:189,199): y = bf16 GEMM operand zero-padded to kpad cols;
  * sets *nonfinite_flag when any token is not finite (encoders.py:197-198). */
 int mca_layernorm_in_fwd(const float* x, const float* w, const float* b, const uint8_t* pad, void* y_bf16,

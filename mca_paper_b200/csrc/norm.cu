@@ -86,14 +86,72 @@ ln512_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
+// Fused "residual add + LayerNorm" (model.py:118-122 wiring, reference quirk Q1: the residual branch starts from the
+// NORMED tensor).  v = LN_prev(xprev) + y  is the new residual-stream value: it is written as fp32 (needed by the
+// backward) and normalised again for the next GEMM operand.  LN_prev is recomputed from xprev and its saved
+// statistics, so the normed tensor itself never goes to HBM in fp32.
+__global__ void __launch_bounds__(256)
+add_ln512_fwd_kernel(const float* __restrict__ xprev, const float2* __restrict__ stats_prev,
+                     const float* __restrict__ gamma_prev, const float* __restrict__ beta_prev,
+                     const __nv_bfloat16* __restrict__ y16, float* __restrict__ xnew, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ out16, float2* __restrict__ stats,
+                     long long rows) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float2 sp = stats_prev[r];
+  float v[16];
+  const float4* x4 = reinterpret_cast<const float4*>(xprev + r * LN_D);
+  const uint2* y2 = reinterpret_cast<const uint2*>(y16 + r * LN_D);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 q = x4[lane + 32 * i];
+    const uint2 yy = y2[lane + 32 * i];
+    const float4 g = *reinterpret_cast<const float4*>(gamma_prev + c);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beta_prev != nullptr) b = *reinterpret_cast<const float4*>(beta_prev + c);
+    v[4 * i] = (q.x - sp.x) * sp.y * g.x + b.x + bf16_lo(yy.x);
+    v[4 * i + 1] = (q.y - sp.x) * sp.y * g.y + b.y + bf16_hi(yy.x);
+    v[4 * i + 2] = (q.z - sp.x) * sp.y * g.z + b.z + bf16_lo(yy.y);
+    v[4 * i + 3] = (q.w - sp.x) * sp.y * g.w + b.w + bf16_hi(yy.y);
+    if (xnew != nullptr)
+      *reinterpret_cast<float4*>(xnew + r * LN_D + c) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  if (out16 == nullptr) return;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / LN_D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = v[i] - mean;
+    ss += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / LN_D) + LN_EPS);
+  if (stats != nullptr && lane == 0) stats[r] = make_float2(mean, rstd);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beta != nullptr) b = *reinterpret_cast<const float4*>(beta + c);
+    uint2 h;
+    h.x = pack_bf16x2((v[4 * i] - mean) * rstd * g.x + b.x, (v[4 * i + 1] - mean) * rstd * g.y + b.y);
+    h.y = pack_bf16x2((v[4 * i + 2] - mean) * rstd * g.z + b.z, (v[4 * i + 3] - mean) * rstd * g.w + b.w);
+    *reinterpret_cast<uint2*>(out16 + r * LN_D + c) = h;
+  }
+}
+
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy.
 // dy is read at the mapped row (gathering the modality's rows out of the packed gradient); rows flagged in `pad`
 // contribute nothing (encoders.py:205 masked_fill blocks their gradient).
 __global__ void __launch_bounds__(256)
-ln512_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float2* __restrict__ stats,
-                 const float* __restrict__ gamma, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16,
-                 float* __restrict__ dgamma, float* __restrict__ dbeta, const uint8_t* __restrict__ pad, RowMap map,
-                 long long rows) {
+ln512_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_delta, const float* __restrict__ x,
+                 const float2* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ dx32,
+                 __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                 const uint8_t* __restrict__ pad, RowMap map, long long rows) {
   __shared__ float sg[8][LN_D];
   __shared__ float sb[8][LN_D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -116,6 +174,10 @@ ln512_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, cons
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float4 q = d4[lane + 32 * i];
+      if (dy_delta != nullptr) {  // gradient that arrived through the branch GEMM (bf16), added to the residual path
+        const uint2 dd = *reinterpret_cast<const uint2*>(dy_delta + rd * LN_D + (lane + 32 * i) * 4);
+        q.x += bf16_lo(dd.x), q.y += bf16_hi(dd.x), q.z += bf16_lo(dd.y), q.w += bf16_hi(dd.y);
+      }
       if (padded) q = make_float4(0.f, 0.f, 0.f, 0.f);
       d[4 * i] = q.x, d[4 * i + 1] = q.y, d[4 * i + 2] = q.z, d[4 * i + 3] = q.w;
       const float4 p = x4[lane + 32 * i];
@@ -255,17 +317,32 @@ extern "C" int mca_layernorm512_fwd(const float* x, const float* gamma, const fl
   return check_launch();
 }
 
-extern "C" int mca_layernorm512_bwd(const float* dy, const float* x, const float* stats, const float* gamma,
-                                    float* dx32, void* dx16, float* dgamma, float* dbeta, const uint8_t* pad,
-                                    int seg_len, int out_rows_per_b, int out_row_off, long long rows, void* stream) {
+extern "C" int mca_layernorm512_bwd(const float* dy, const void* dy_delta_bf16, const float* x, const float* stats,
+                                    const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta,
+                                    const uint8_t* pad, int seg_len, int out_rows_per_b, int out_row_off, long long rows,
+                                    void* stream) {
   if (rows <= 0) return MCA_ERR_SHAPE;
   RowMap map{seg_len, out_rows_per_b, out_row_off};
   long long want = (rows + 7) / 8;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   ln512_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      dy, x, reinterpret_cast<const float2*>(stats), gamma, dx32, reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta,
-      pad, map, rows);
+      dy, reinterpret_cast<const __nv_bfloat16*>(dy_delta_bf16), x, reinterpret_cast<const float2*>(stats), gamma, dx32,
+      reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta, pad, map, rows);
+  return check_launch();
+}
+
+extern "C" int mca_add_layernorm512_fwd(const float* xprev, const float* stats_prev, const float* gamma_prev,
+                                        const float* beta_prev, const void* y_bf16, float* xnew, const float* gamma,
+                                        const float* beta, void* out_bf16, float* stats, long long rows, void* stream) {
+  if (rows <= 0) return MCA_ERR_SHAPE;
+  if (xprev == nullptr || stats_prev == nullptr || gamma_prev == nullptr || y_bf16 == nullptr) return MCA_ERR_ARG;
+  if (out_bf16 != nullptr && gamma == nullptr) return MCA_ERR_ARG;
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  add_ln512_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      xprev, reinterpret_cast<const float2*>(stats_prev), gamma_prev, beta_prev,
+      reinterpret_cast<const __nv_bfloat16*>(y_bf16), xnew, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+      reinterpret_cast<float2*>(stats), rows);
   return check_launch();
 }
 

@@ -194,7 +194,8 @@ class Engine:
         ws["x3_16"] = [b16(M, D) for _ in range(L)]
         ws["u"] = [b16(M, 2 * IP) for _ in range(L)]
         ws["h"] = [b16(M, IP) for _ in range(L)]
-        ws["x1_32"], ws["x3_32"] = f32(M, D), f32(M, D)
+        ws["y16"] = b16(M, D)    # branch output of out-proj / FF2 (consumed at once by the fused add + LayerNorm)
+        ws["dy16"] = b16(M, D)   # branch gradient of the dX GEMMs (added inside the LayerNorm backward)
         ws["stF"], ws["xf_16"], ws["kvp"] = f32(M, 2), b16(M, D), b16(M, 2 * D)
         ws["qp"], ws["probs"], ws["fm"] = f32(R, D), f32(B, H, R, N), u8(B, R)
         ws["po"], ws["pooled"] = f32(B, R, D), f32(B, R, D)
@@ -324,21 +325,32 @@ class Engine:
         ws["nonfinite"].zero_()
         self.build_offsets(batch)
         self.encode(batch)
+        # Residual wiring of model.py:117-122 (quirk Q1): x1 = LN(x); x2 = attn(x1) + x1; x3 = LN(x2); x' = ff(x3) + x3,
+        # with ONE LayerNorm per layer.  The branch GEMMs write bf16; the residual add is fused with the NEXT LayerNorm,
+        # which recomputes the normed residual from (x, stats) instead of reading an fp32 copy of it.
+        gamma0, beta0 = self.pview("layers.0.norm.gamma"), self.model.layers[0].norm.beta
+        ops.layernorm512_fwd(ws["xa"][0], gamma0, beta0, None, ws["x1_16"][0], ws["st1"][0], M)
         for l in range(self.depth):
             p = f"layers.{l}."
             gamma, beta = self.pview(p + "norm.gamma"), self.model.layers[l].norm.beta
-            ops.layernorm512_fwd(ws["xa"][l], gamma, beta, ws["x1_32"], ws["x1_16"][l], ws["st1"][l], M)
             ops.gemm(ws["x1_16"][l], 0, self.W(p + "qkv"), 0, M, 3 * D, D, _lib.EPI_BF16, ws["qkv"][l])
             self.attention_fwd(ws["qkv"][l], ws["ao"][l], ws["lse"][l])
-            ops.gemm(ws["ao"][l], 0, self.W(p + "out"), 0, M, D, D, _lib.EPI_RESID, ws["x2"][l], aux0=ws["x1_32"], ldaux=D)
-            ops.layernorm512_fwd(ws["x2"][l], gamma, beta, ws["x3_32"], ws["x3_16"][l], ws["st2"][l], M)
+            ops.gemm(ws["ao"][l], 0, self.W(p + "out"), 0, M, D, D, _lib.EPI_BF16, ws["y16"])
+            # x2 = LN(x) + y ; x3_16 = LN(x2)
+            ops.add_layernorm512_fwd(ws["xa"][l], ws["st1"][l], gamma, beta, ws["y16"], ws["x2"][l], gamma, beta,
+                                     ws["x3_16"][l], ws["st2"][l], M)
             ops.gemm(ws["x3_16"][l], 0, self.W(p + "ff1"), 0, M, 2 * IP, D, _lib.EPI_GEGLU, ws["h"][l], ld0=IP,
                      out1=ws["u"][l], ld1=2 * IP)
-            ops.gemm(ws["h"][l], 0, self.W(p + "ff2"), 0, M, D, IP, _lib.EPI_RESID, ws["xa"][l + 1], aux0=ws["x3_32"],
-                     ldaux=D)
-        # final norm + attention pooling (model.py:470-473)
-        ops.layernorm512_fwd(ws["xa"][self.depth], self.pview("norm.gamma"), self.model.norm.beta, None, ws["xf_16"],
-                             ws["stF"], M)
+            ops.gemm(ws["h"][l], 0, self.W(p + "ff2"), 0, M, D, IP, _lib.EPI_BF16, ws["y16"])
+            # x' = LN(x2) + y ; next operand = LN_next(x') (next layer's norm, or the final norm)
+            if l + 1 < self.depth:
+                gn, bn = self.pview(f"layers.{l + 1}.norm.gamma"), self.model.layers[l + 1].norm.beta
+                ops.add_layernorm512_fwd(ws["x2"][l], ws["st2"][l], gamma, beta, ws["y16"], ws["xa"][l + 1], gn, bn,
+                                         ws["x1_16"][l + 1], ws["st1"][l + 1], M)
+            else:
+                ops.add_layernorm512_fwd(ws["x2"][l], ws["st2"][l], gamma, beta, ws["y16"], ws["xa"][l + 1],
+                                         self.pview("norm.gamma"), self.model.norm.beta, ws["xf_16"], ws["stF"], M)
+        # attention pooling on the final-normed tokens (model.py:470-473)
         ops.gemm(ws["xf_16"], 0, self.W("attn_pool.kv"), 0, M, 2 * D, D, _lib.EPI_BF16, ws["kvp"])
         rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
         ops.small_gemm(rt, D, 1, wq, D, 1, ws["qp"], D, self.R, D, D, alpha=DH ** -0.5)
@@ -416,16 +428,19 @@ class Engine:
             ops.gemm(ws["d16"], 0, self.W(p + "ff2"), 1, M, IP, D, _lib.EPI_GEGLU_BWD, ws["du"], ld0=2 * IP,
                      aux0=ws["u"][l], ldaux=2 * IP)
             self._dw(p + "ff2", ws["d16"], ws["h"][l], D, IP, M)
-            ops.gemm(ws["du"], 0, self.W(p + "ff1"), 1, M, D, 2 * IP, _lib.EPI_RESID, dx_alt, aux0=dx, ldaux=D)  # dx3
+            ops.gemm(ws["du"], 0, self.W(p + "ff1"), 1, M, D, 2 * IP, _lib.EPI_BF16, ws["dy16"])   # branch part of dx3
             self._dw(p + "ff1", ws["du"], ws["x3_16"][l], 2 * IP, D, M)
-            ops.layernorm512_bwd(dx_alt, ws["x2"][l], ws["st2"][l], gamma, dx, ws["d16"], dgamma, None, M)       # dx2
+            # dx3 = dx (residual path) + dy16 (branch); LayerNorm backward -> dx2
+            ops.layernorm512_bwd(dx, ws["x2"][l], ws["st2"][l], gamma, dx_alt, ws["d16"], dgamma, None, M, dy_delta=ws["dy16"])
+            dx, dx_alt = dx_alt, dx
             # x2 = ao Wo^T + x1
             ops.gemm(ws["d16"], 0, self.W(p + "out"), 1, M, D, D, _lib.EPI_BF16, ws["dattn"])
             self._dw(p + "out", ws["d16"], ws["ao"][l], D, D, M)
             self.attention_bwd(l)
-            ops.gemm(ws["dqkv"], 0, self.W(p + "qkv"), 1, M, D, 3 * D, _lib.EPI_RESID, dx_alt, aux0=dx, ldaux=D)  # dx1
+            ops.gemm(ws["dqkv"], 0, self.W(p + "qkv"), 1, M, D, 3 * D, _lib.EPI_BF16, ws["dy16"])      # branch part of dx1
             self._dw(p + "qkv", ws["dqkv"], ws["x1_16"][l], 3 * D, D, M)
-            ops.layernorm512_bwd(dx_alt, ws["xa"][l], ws["st1"][l], gamma, dx, ws["d16"], dgamma, None, M)       # dx0
+            ops.layernorm512_bwd(dx, ws["xa"][l], ws["st1"][l], gamma, dx_alt, ws["d16"], dgamma, None, M, dy_delta=ws["dy16"])
+            dx, dx_alt = dx_alt, dx
         self.encode_backward(dx)
         call("mca_unpack_grads", P(self.flat_grad), P(self.garena), P(self.unpack_descs), self.n_desc, S())
 

@@ -31,7 +31,8 @@ _SIGS = {
     "mca_gemm_bf16": [VP, I32, I64, VP, I32, I64, I32, I32, I32, I32, I32, VP, I64, VP, I64, VP, I64, VP, F32, VP],
     "mca_build_offsets": [VP, VP, VP, I32, I32, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP],
     "mca_layernorm512_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I64, VP],
-    "mca_layernorm512_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I64, VP],
+    "mca_layernorm512_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I64, VP],
+    "mca_add_layernorm512_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, I64, VP],
     "mca_layernorm_in_fwd": [VP, VP, VP, VP, VP, VP, I32, I32, I64, VP, VP],
     "mca_layernorm_in_param_bwd": [VP, I32, VP, VP, VP, VP, VP, I32, I64, VP],
     "mca_colsum": [VP, I32, VP, I32, I64, VP],
@@ -124,9 +125,14 @@ def layernorm512_fwd(x, gamma, beta, y32, y16, stats, rows, pad=None, pe=None, s
 
 
 def layernorm512_bwd(dy, x, stats, gamma, dx32, dx16, dgamma, dbeta, rows, pad=None, seg_len=0, out_rows_per_b=0,
-                     out_row_off=0):
-    call("mca_layernorm512_bwd", P(dy), P(x), P(stats), P(gamma), P(dx32), P(dx16), P(dgamma), P(dbeta), P(pad),
-         int(seg_len), int(out_rows_per_b), int(out_row_off), int(rows), S())
+                     out_row_off=0, dy_delta=None):
+    call("mca_layernorm512_bwd", P(dy), P(dy_delta), P(x), P(stats), P(gamma), P(dx32), P(dx16), P(dgamma), P(dbeta),
+         P(pad), int(seg_len), int(out_rows_per_b), int(out_row_off), int(rows), S())
+
+
+def add_layernorm512_fwd(xprev, stats_prev, gamma_prev, beta_prev, y16, xnew, gamma, beta, out16, stats, rows):
+    call("mca_add_layernorm512_fwd", P(xprev), P(stats_prev), P(gamma_prev), P(beta_prev), P(y16), P(xnew), P(gamma),
+         P(beta), P(out16), P(stats), int(rows), S())
 
 
 def small_gemm(A, sam, sak, Bm, sbn, sbk, Cm, ldc, M, N, K, alpha=1.0, accumulate=False, add=None, ldadd=0, add_rows=0):

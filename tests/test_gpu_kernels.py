@@ -124,6 +124,35 @@ def test_layernorm512_fwd_bwd():
     assert rel_err(dx, xr.grad) < 1e-4 and rel_err(dg, gr.grad) < 1e-4 and rel_err(dx16, xr.grad) < 5e-3
 
 
+def test_add_layernorm_fused_residual_and_delta_backward():
+    """x_new = LN(x_prev) + y (quirk Q1 residual) fused with the next LayerNorm; backward with a bf16 branch delta."""
+    torch.manual_seed(4)
+    rows = 2049
+    xp = torch.randn(rows, 512, device=dev) * 1.5 - 0.2
+    g0, g1 = torch.rand(512, device=dev) + 0.5, torch.rand(512, device=dev) + 0.5
+    beta = torch.zeros(512, device=dev)
+    st0 = torch.empty(rows, 2, device=dev)
+    tmp16 = torch.empty(rows, 512, device=dev, dtype=torch.bfloat16)
+    ops.layernorm512_fwd(xp, g0, beta, None, tmp16, st0, rows)
+    y = (torch.randn(rows, 512, device=dev) * 0.7).bfloat16()
+    xnew = torch.empty_like(xp)
+    out16 = torch.empty(rows, 512, device=dev, dtype=torch.bfloat16)
+    st1 = torch.empty(rows, 2, device=dev)
+    ops.add_layernorm512_fwd(xp, st0, g0, beta, y, xnew, g1, beta, out16, st1, rows)
+    ref_new = torch.nn.functional.layer_norm(xp, (512,), g0, beta) + y.float()
+    assert rel_err(xnew, ref_new) < 1e-5
+    assert rel_err(out16, torch.nn.functional.layer_norm(ref_new, (512,), g1, beta)) < 5e-3
+    # backward: dy (fp32 residual path) + delta (bf16 branch path)
+    xr = ref_new.clone().requires_grad_(True)
+    dy = torch.randn_like(xp)
+    dd = (torch.randn_like(xp) * 0.5).bfloat16()
+    torch.nn.functional.layer_norm(xr, (512,), g1, beta).backward(dy + dd.float())
+    dx = torch.empty_like(xp)
+    dg = torch.zeros(512, device=dev)
+    ops.layernorm512_bwd(dy, xnew, st1, g1, dx, None, dg, None, rows, dy_delta=dd)
+    assert rel_err(dx, xr.grad) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ offsets
 @pytest.mark.parametrize("cfg_name,variant", [("CMU_config1_d40", "dropout_ragged"), ("TCGA_config1", "tcga")])
 def test_build_offsets_bit_exact(cfg_name, variant):
