@@ -37,7 +37,8 @@ enum {
   MCA_EPI_F32 = 1,       /* out0(f32)[z] = alpha*acc + bias, one slab per k-split z */
   MCA_EPI_RESID = 2,     /* out0(f32) = alpha*acc + aux0(f32); optional out1(bf16) copy */
   MCA_EPI_GEGLU = 3,     /* out1(bf16) = u = acc (interleaved value|gate), out0(bf16) = gelu(gate)*value */
-  MCA_EPI_GEGLU_BWD = 4  /* acc = dL/dh, aux0 = u; out0(bf16) = dL/du */
+  MCA_EPI_GEGLU_BWD = 4, /* acc = dL/dh, aux0 = u; out0(bf16) = dL/du */
+  MCA_EPI_F32_ACC = 5    /* out0(f32) += alpha*acc: every k-split reduce-adds (TMA) into ONE slab the caller zeroed */
 };
 
 /* ---- static attention schedule (host-built once from token_types / attn_mask, model.py:383-430) ---- */

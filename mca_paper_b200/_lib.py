@@ -9,12 +9,13 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmca_b200.so")
+# MCA_LIB selects another build of the SAME library (e.g. the -DMCA_TRACE debug build); there is still no fallback
+LIB_PATH = os.environ.get("MCA_LIB") or os.path.join(_HERE, "csrc", "libmca_b200.so")
 
 MCA_OK = 0
 ERR_NAMES = {1: "MCA_ERR_SHAPE", 2: "MCA_ERR_ALIGN", 3: "MCA_ERR_CUDA", 4: "MCA_ERR_NONFINITE", 5: "MCA_ERR_ARG"}
 
-EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_GEGLU_BWD = range(5)
+EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_GEGLU_BWD, EPI_F32_ACC = range(6)
 
 _lib = None
 

@@ -11,8 +11,12 @@
 //     Y(t,h): dV  += P^T dO_h         dK  += dS^T Q_h            (A from TMEM, B = the TMA tiles read MN-major)
 //     Z(t)  : dQ   = dS K             (128 x 64 x 128; fresh tile -> fp32 smem -> TMA reduce-add into dq_acc)
 // dK/dV stay resident in TMEM across the whole loop and are written once.  Q/dO tiles are double buffered.
+// The per-query terms ride on the tensor core: both score products get one extra k-step whose B rows hold
+// (-lse, -delta) of the query, each split into three bf16 terms (exact to 2^-25), against constant 0/1 A rows, so
+// the accumulators arrive as S^T - lse_q and dP^T - delta_q and the compute warps never load a per-query value
+// (those broadcast shared-memory loads were a third of the kernel's shared-memory traffic, which is what bounds it).
 // Masking costs nothing per element for the common tiles: a query that may not see this tile's key group gets
-// lse = +inf (P = 0) when its lse is staged; only tiles with padded / missing keys or mixed key groups (the fusion
+// -lse = -60000 (P = 0) in that row; only tiles with padded / missing keys or mixed key groups (the fusion
 // sub-blocks) take a per-element select.  Fully masked query rows carry lse = +inf from the forward; their
 // uniform-1/N contribution to dV (reference quirk Q4) is the per-(sample, head) vector `ucorr`, added in the epilogue.
 #include <math_constants.h>
@@ -32,7 +36,13 @@ constexpr int AB_DQ = AB_T * AB_DH * 4;    // 32 KB fp32 [128, 64]
 constexpr int AB_QSTAGES = 3;
 constexpr int AB_MAX_ITERS = 64;  // query tiles attending one key tile
 // sK, sV, 3x(sQ, sdO), sdS (half 0 double buffered, half 1 single), sdQ; per-query staging and barriers are static
-constexpr int AB_SMEM = 2 * AB_TILE + 2 * AB_QSTAGES * AB_TILE + 3 * (AB_DS / 2) + AB_DQ;
+// extra k-step operands (K-major, no swizzle: 8-row x 16-byte core matrices, 128 B between the two k chunks, 256 B
+// between 8-row groups): A rows for S^T [128 x 16], A rows for dP^T [128 x 16], B rows per query half [64 x 16] x 2
+constexpr int AB_EXT_A = AB_T * 32;
+constexpr int AB_EXT_B = 64 * 32;
+constexpr int AB_EXT = 2 * AB_EXT_A + 2 * AB_EXT_B;
+constexpr int AB_SMEM = 2 * AB_TILE + 2 * AB_QSTAGES * AB_TILE + 3 * (AB_DS / 2) + AB_DQ + AB_EXT;
+constexpr float AB_MASKED = -60000.f;  // -lse of a query that must not see this key tile: exp2 underflows to 0
 constexpr float AB_LOG2E = 1.4426950408889634f;
 
 struct AttnBwdArgs {
@@ -63,12 +73,6 @@ __device__ long long g_trace[4 * 16 * 16 + 8];
 #define TRG(e) do { } while (0)
 #endif
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_dq, const AttnBwdArgs a) {
@@ -79,9 +83,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sdO = sQ + AB_QSTAGES * AB_TILE;   // AB_QSTAGES stages
   uint8_t* sdS = sdO + AB_QSTAGES * AB_TILE;  // [half 0, buffer 0][half 0, buffer 1][half 1], 16 KB each
   uint8_t* sdQ = sdS + 3 * (AB_DS / 2);       // two 32-column fp32 boxes
+  uint8_t* sAS = sdQ + AB_DQ;                 // extra k-step: A rows of the S^T product (ones in k = 0..2)
+  uint8_t* sAD = sAS + AB_EXT_A;              //               A rows of the dP^T product (ones in k = 3..5)
+  uint8_t* sBX = sAD + AB_EXT_A;              //               B rows [half][query]: -lse (k 0..2), -delta (k 3..5)
   __shared__ int2 s_qt[AB_MAX_ITERS];                 // (start, len) of every query tile this CTA visits
-  __shared__ __align__(16) float s_lse[2][2][64];     // [half][buffer][query]: -lse*log2e, -inf = masked
-  __shared__ __align__(16) float s_dl[2][2][64];      // -delta
   __shared__ __align__(16) uint32_t s_rb[2][2][64];   // allowed-key-group bits (mixed-group tiles only)
   __shared__ uint64_t bars[24];
   __shared__ uint32_t tmem_holder_s;
@@ -91,11 +96,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint64_t* x_full = bars + 7;     // [2] per half: S^T / dP^T of the half are in TMEM
   uint64_t* x_free = bars + 9;     // [2] per half: the compute warpgroup has copied them to registers
   uint64_t* c_done = bars + 11;    // [2] per half: P^T / dS^T written (TMEM + smem)
-  uint64_t* y_done = bars + 13;    // dV / dK products of one half retired: the P^T / dS^T columns are free
-  uint64_t* z_full = bars + 14;    // [2] by tile parity: dQ product retired (dS consumed, dQ accumulator complete)
-  uint64_t* dq_free = bars + 16;   // dQ accumulator copied to registers
-  uint64_t* sdq_full = bars + 17;  // dQ tile staged in shared memory
-  uint64_t* sdq_free = bars + 18;  // the TMA reduce has finished reading the staged tile
+  uint64_t* y_done = bars + 13;    // [2] per half: its dV / dK products retired, the shared P^T / dS^T columns are free
+                                   // (one barrier per half: a waiter can then never be a whole phase ahead of it)
+  uint64_t* z_full = bars + 15;    // [2] by tile parity: dQ product retired (dS consumed, dQ accumulator complete)
+  uint64_t* dq_free = bars + 17;   // dQ accumulator copied to registers
+  uint64_t* sdq_full = bars + 18;  // dQ tile staged in shared memory
+  uint64_t* sdq_free = bars + 19;  // the TMA reduce has finished reading the staged tile
   uint32_t* tmem_holder = &tmem_holder_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,7 +120,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_init(kv_full, 1);
     for (int s = 0; s < AB_QSTAGES; ++s) mbar_init(&qdo_full[s], 1), mbar_init(&qdo_empty[s], 1);
     for (int s = 0; s < 2; ++s) mbar_init(&x_full[s], 1), mbar_init(&x_free[s], 128), mbar_init(&c_done[s], 128);
-    mbar_init(y_done, 1);
+    mbar_init(&y_done[0], 1), mbar_init(&y_done[1], 1);
     mbar_init(&z_full[0], 1), mbar_init(&z_full[1], 1);
     mbar_init(dq_free, 128);
     mbar_init(sdq_full, 128);
@@ -125,6 +131,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   for (int i = threadIdx.x; i < n_iter; i += AB_THREADS) {
     const mca_attn_tile Q = a.q_tiles[a.qt_list[KT.kt_off + i].tile];
     s_qt[i] = make_int2(Q.start, Q.len);
+  }
+  if (threadIdx.x < 256) {  // constant rows of the extra k-step (bf16 1.0 = 0x3F80); the second k chunk is all zero
+    const int row = threadIdx.x & 127, which = threadIdx.x >> 7;
+    uint8_t* dst = (which == 0 ? sAS : sAD) + (row >> 3) * 256 + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = which == 0 ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u)
+                                                : make_uint4(0u, 0x3F800000u, 0x3F803F80u, 0u);
+    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+    if (row < 64) *reinterpret_cast<uint4*>(sBX + which * AB_EXT_B + (row >> 3) * 256 + 128 + (row & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -189,15 +204,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const uint64_t do_k0 = make_smem_desc_sw128(smem_u32(sdO), 16, 1024);
       const uint64_t dq_mn0 = make_smem_desc_sw128(smem_u32(sQ), 8192, 1024);
       const uint64_t do_mn0 = make_smem_desc_sw128(smem_u32(sdO), 8192, 1024);
+      const uint64_t d_as = make_smem_desc_nosw(smem_u32(sAS), 128, 256);
+      const uint64_t d_ad = make_smem_desc_nosw(smem_u32(sAD), 128, 256);
+      const uint64_t d_bx = make_smem_desc_nosw(smem_u32(sBX), 128, 256);
       auto issue_x = [&](int t, int hf) {
         const uint64_t off = static_cast<uint64_t>(((t % AB_QSTAGES) * AB_TILE + hf * 8192) >> 4);
         const uint32_t reg = tmem_base + hf * 128;
+        const uint64_t bx = d_bx + static_cast<uint64_t>((hf * AB_EXT_B) >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < AB_DH / 16; ++k) {
             umma_bf16(reg, dk_k + k * 2, dq_k0 + off + k * 2, id_x, k > 0 ? 1u : 0u);
             umma_bf16(reg + 64, dv_k + k * 2, do_k0 + off + k * 2, id_x, k > 0 ? 1u : 0u);
           }
+          umma_bf16(reg, d_as, bx, id_x, 1u);        // S^T  -= lse_q
+          umma_bf16(reg + 64, d_ad, bx, id_x, 1u);   // dP^T -= delta_q
           umma_commit(&x_full[hf]);
         }
         __syncwarp();
@@ -212,7 +233,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             umma_bf16_ts(tdV, tP + k * 8, do_mn0 + off + k * 128, id_y, k > 0 ? 1u : acc);
             umma_bf16_ts(tdK, tP + 32 + k * 8, dq_mn0 + off + k * 128, id_y, k > 0 ? 1u : acc);
           }
-          umma_commit(y_done);
+          umma_commit(&y_done[hf]);
           if (last_of_tile) umma_commit(&qdo_empty[t % AB_QSTAGES]);  // Q / dO of this tile are no longer read
         }
         __syncwarp();
@@ -221,8 +242,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       if (lane == 0) TRG(1);
       mbar_wait(&qdo_full[0], 0);
       if (lane == 0) TRG(2);
+      // x_free[h] phase n = "the B rows of tile n are written and S^T / dP^T of tile n-1 have been read"
+      mbar_wait(&x_free[0], 0);
       tc_fence_after();
       issue_x(0, 0);
+      mbar_wait(&x_free[1], 0);
+      tc_fence_after();
       issue_x(0, 1);
       for (int t = 0; t < n_iter; ++t) {
         const uint32_t ph = t & 1;
@@ -230,7 +255,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         if (lane == 0) TR(2, t, 0);
         if (more) {
           mbar_wait(&qdo_full[(t + 1) % AB_QSTAGES], ((t + 1) / AB_QSTAGES) & 1);
-          mbar_wait(&x_free[0], ph);  // S^T_0 / dP^T_0 of tile t are in registers: overwrite them right away
+          mbar_wait(&x_free[0], ph ^ 1);  // S^T_0 / dP^T_0 of tile t are in registers: overwrite them right away
           tc_fence_after();
           issue_x(t + 1, 0);
         }
@@ -241,7 +266,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         issue_y(t, 0, false);
         if (lane == 0) TR(2, t, 3);
         if (more) {
-          mbar_wait(&x_free[1], ph);
+          mbar_wait(&x_free[1], ph ^ 1);
           tc_fence_after();
           issue_x(t + 1, 1);
         }
@@ -288,15 +313,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
     const bool dead = has_dead && !live;
     const long long sbase = (static_cast<long long>(b) * a.H + h) * a.N;
-    // raw per-query values of tile t go global -> shared with cp.async (no registers held across an iteration)
-    auto stage_async = [&](int t) {
+    // Per-query values: the first 64 threads of each warpgroup own one query of the half.  They load (lse, delta,
+    // allowed-group bits) one tile ahead into registers and turn them into the B row of the extra k-step.
+    float r_lse = CUDART_INF_F, r_dl = 0.f;
+    uint32_t r_rb = 0u;
+    auto load_q = [&](int t) {
       if (wt < 64 && t < n_iter) {
         const int qi = min(s_qt[t].x + hf * 64 + wt, a.N - 1);
-        cp_async4(&s_lse[hf][t & 1][wt], a.lse + sbase + qi);
-        cp_async4(&s_dl[hf][t & 1][wt], a.delta + sbase + qi);
-        cp_async4(&s_rb[hf][t & 1][wt], a.rowbits + qi);
+        r_lse = a.lse[sbase + qi];
+        r_dl = a.delta[sbase + qi];
+        r_rb = a.rowbits[qi];
       }
-      cp_async_commit();
+    };
+    auto split3 = [](float v, uint32_t& h, uint32_t& m, uint32_t& l) {  // v = h + m + l in bf16 terms
+      const __nv_bfloat16 bh = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(bh);
+      const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 bl = __float2bfloat16_rn(r1 - __bfloat162float(bm));
+      h = __bfloat16_as_ushort(bh), m = __bfloat16_as_ushort(bm), l = __bfloat16_as_ushort(bl);
+    };
+    auto write_ext = [&](int t) {  // B row of this thread's query for tile t (from the registers loaded for t)
+      if (wt < 64 && t < n_iter) {
+        const bool valid = hf * 64 + wt < s_qt[t].y;
+        const uint32_t rb = valid ? r_rb : 0u;
+        const bool sees = valid && (kgrp == 255 || ((rb >> kgrp) & 1u)) && r_lse != CUDART_INF_F;
+        uint32_t lh, lm, ll, dh, dm, dl;
+        split3(sees ? -r_lse : AB_MASKED, lh, lm, ll);
+        split3(valid ? -r_dl : 0.f, dh, dm, dl);
+        *reinterpret_cast<uint4*>(sBX + hf * AB_EXT_B + (wt >> 3) * 256 + (wt & 7) * 16) =
+            make_uint4(lh | (lm << 16), ll | (dh << 16), dm | (dl << 16), 0u);
+        if (kgrp == 255) s_rb[hf][t & 1][wt] = rb;
+        fence_proxy_async_smem();
+      }
     };
     auto drain_dq = [&](int tp) {  // dQ of tile tp: TMEM -> registers -> fp32 swizzled smem (the reduce warp ships it)
       mbar_wait(&z_full[tp & 1], (tp >> 1) & 1);
@@ -317,23 +365,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       fence_proxy_async_smem();
       mbar_arrive(sdq_full);
     };
-    stage_async(0);
+    load_q(0);
+    write_ext(0);
+    load_q(1);
+    mbar_arrive(&x_free[hf]);  // phase 0: the B rows of tile 0 are in place
     for (int t = 0; t < n_iter; ++t) {
       const uint32_t ph = t & 1;
       if (wt == 0) TR(hf, t, 0);
-      cp_async_wait_all();
-      if (wt < 64) {  // fix up the staged values in place: fold the group mask into lse, pre-negate for the FMAs
-        const int qr = hf * 64 + wt;
-        const bool valid = qr < s_qt[t].y;
-        const uint32_t rb = valid ? s_rb[hf][t & 1][wt] : 0u;
-        const bool sees = valid && (kgrp == 255 || ((rb >> kgrp) & 1u));
-        s_lse[hf][t & 1][wt] = sees ? -s_lse[hf][t & 1][wt] * AB_LOG2E : -CUDART_INF_F;
-        s_dl[hf][t & 1][wt] = valid ? -s_dl[hf][t & 1][wt] : 0.f;
-        s_rb[hf][t & 1][wt] = rb;
-      }
-      ab_bar_sync(1 + hf, 128);
-      stage_async(t + 1);  // after the barrier: every thread is done with the other buffer (tile t-1)
-      if (wt == 0) TR(hf, t, 1);
       mbar_wait(&x_full[hf], ph);
       if (wt == 0) TR(hf, t, 2);
       tc_fence_after();
@@ -342,26 +380,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tmem_ld32(reg + 32, sv[1]);
       tmem_ld32(reg + 64, dv[0]);
       tmem_ld32(reg + 96, dv[1]);
+      // mixed-group key tiles read the queries' group bits from shared memory: everyone is done with the buffer that
+      // write_ext(t + 1) overwrites, and the bits of tile t (written one iteration ago) become visible
+      if (kgrp == 255) ab_bar_sync(1 + hf, 128);
+      write_ext(t + 1);  // X(t) has retired (x_full): its B rows may be replaced
+      load_q(t + 2);
       tmem_ld_wait();
       if (wt == 0) TR(hf, t, 3);
       tc_fence_before();
       mbar_arrive(&x_free[hf]);  // the next tile's S^T / dP^T of this half may be issued now
-      const float4* lse4 = reinterpret_cast<const float4*>(s_lse[hf][t & 1]);
-      const float4* dl4 = reinterpret_cast<const float4*>(s_dl[hf][t & 1]);
       const uint32_t* rbq = s_rb[hf][t & 1];
-      // P^T = exp2(S^T*log2e - lse2[q]),  dS^T = P^T * (dP^T - delta[q])   (in place in sv / dv)
+      // accumulators already hold S^T - lse[q] and dP^T - delta[q]:  P^T = exp2(log2e * .),  dS^T = P^T * (.)
 #pragma unroll
-      for (int g = 0; g < 16; ++g) {
-        const float4 l4 = lse4[g], d4 = dl4[g];
-        const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = g * 4 + i;
-          const float pi = fast_ex2(fmaf(__uint_as_float(sv[e >> 5][e & 31]), AB_LOG2E, lq[i]));
-          const float di = pi * (__uint_as_float(dv[e >> 5][e & 31]) + dq[i]);
-          sv[e >> 5][e & 31] = __float_as_uint(pi);
-          dv[e >> 5][e & 31] = __float_as_uint(di);
-        }
+      for (int e = 0; e < 64; ++e) {
+        const float pi = fast_ex2(__uint_as_float(sv[e >> 5][e & 31]) * AB_LOG2E);
+        sv[e >> 5][e & 31] = __float_as_uint(pi);
+        dv[e >> 5][e & 31] = __float_as_uint(pi * __uint_as_float(dv[e >> 5][e & 31]));
       }
       if (kgrp == 255) {  // mixed key groups (fusion sub-blocks): per-(query, key) visibility
 #pragma unroll
@@ -394,10 +428,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(ds_row + ((c ^ (r & 7)) << 4)) = make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
       // the P^T / dS^T columns are shared by both halves: wait until the previous half's dV / dK products retired
-      const int yk = 2 * t + hf - 1;  // index of that commit on y_done
       if (wt == 0) TR(hf, t, 4);
-      if (yk >= 0) {
-        mbar_wait(y_done, yk & 1);
+      if (hf == 1) {  // half 1 of tile t follows half 0 of tile t; half 0 of tile t follows half 1 of tile t - 1
+        mbar_wait(&y_done[0], ph);
+        tc_fence_after();
+      } else if (t > 0) {
+        mbar_wait(&y_done[1], ph ^ 1);
         tc_fence_after();
       }
       if (wt == 0) TR(hf, t, 5);

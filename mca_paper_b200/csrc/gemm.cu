@@ -36,6 +36,7 @@ struct GemmParams {
   int M, N, K;
   int k_splits;
   int mode;
+  int reduce;  // MCA_EPI_F32 only: TMA reduce-add into slab 0 instead of a store into slab z
   const float* bias;
   float alpha;
 };
@@ -270,8 +271,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async_smem();
         __syncwarp();
         if (elect_one()) {
-          tma_store_3d(&tmO0, stg, n0 + hf * 64, row0, z);
-          tma_store_3d(&tmO0, stg + 4096, n0 + hf * 64 + 32, row0, z);
+          if (p.reduce) {
+            tma_reduce_add_3d(&tmO0, stg, n0 + hf * 64, row0, 0);
+            tma_reduce_add_3d(&tmO0, stg + 4096, n0 + hf * 64 + 32, row0, 0);
+          } else {
+            tma_store_3d(&tmO0, stg, n0 + hf * 64, row0, z);
+            tma_store_3d(&tmO0, stg + 4096, n0 + hf * 64 + 32, row0, z);
+          }
           bulk_commit_group();
         }
       } else if (p.mode == MCA_EPI_GEGLU) {
@@ -385,8 +391,8 @@ extern "C" int mca_gemm_bf16(const void* A, int a_mn_major, long long lda, const
                              float alpha, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0 || k_splits < 1 || (N % 32) != 0) return MCA_ERR_SHAPE;
-  if (mode < MCA_EPI_BF16 || mode > MCA_EPI_GEGLU_BWD || out0 == nullptr) return MCA_ERR_ARG;
-  if (mode != MCA_EPI_F32 && k_splits != 1) return MCA_ERR_SHAPE;
+  if (mode < MCA_EPI_BF16 || mode > MCA_EPI_F32_ACC || out0 == nullptr) return MCA_ERR_ARG;
+  if (mode != MCA_EPI_F32 && mode != MCA_EPI_F32_ACC && k_splits != 1) return MCA_ERR_SHAPE;
   if ((mode == MCA_EPI_GEGLU && (out1 == nullptr || (N % 128) != 0)) ||
       ((mode == MCA_EPI_RESID || mode == MCA_EPI_GEGLU_BWD) && aux0 == nullptr) ||
       (mode == MCA_EPI_GEGLU_BWD && (N % 64) != 0))
@@ -410,8 +416,8 @@ extern "C" int mca_gemm_bf16(const void* A, int a_mn_major, long long lda, const
     const uint64_t dims[2] = {uN, uM}, st[1] = {(uint64_t)ld0};
     const uint32_t box[2] = {64, 32};
     rc = make_tmap(&tmO0, 2, out0, 2, dims, st, box, 128);
-  } else if (mode == MCA_EPI_F32 || mode == MCA_EPI_RESID) {
-    const uint64_t dims[3] = {uN, uM, (uint64_t)k_splits}, st[2] = {(uint64_t)ld0, uM * (uint64_t)ld0};
+  } else if (mode == MCA_EPI_F32 || mode == MCA_EPI_RESID || mode == MCA_EPI_F32_ACC) {
+    const uint64_t dims[3] = {uN, uM, (uint64_t)(mode == MCA_EPI_F32_ACC ? 1 : k_splits)}, st[2] = {(uint64_t)ld0, uM * (uint64_t)ld0};
     const uint32_t box[3] = {32, 32, 1};
     rc = make_tmap(&tmO0, 4, out0, 3, dims, st, box, 128);
   } else if (mode == MCA_EPI_GEGLU) {
@@ -440,7 +446,9 @@ extern "C" int mca_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   }
   if (rc != MCA_OK) return rc;
   GemmParams p;
-  p.M = M, p.N = N, p.K = K, p.k_splits = k_splits, p.mode = mode, p.bias = bias, p.alpha = alpha;
+  p.M = M, p.N = N, p.K = K, p.k_splits = k_splits, p.bias = bias, p.alpha = alpha;
+  p.reduce = mode == MCA_EPI_F32_ACC ? 1 : 0;
+  p.mode = mode == MCA_EPI_F32_ACC ? static_cast<int>(MCA_EPI_F32) : mode;
   if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(tmA, tmB, tmO0, tmO1, tmAux, p, stream);
   if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(tmA, tmB, tmO0, tmO1, tmAux, p, stream);
   if (a_mn_major && b_mn_major) return launch_gemm<true, true>(tmA, tmB, tmO0, tmO1, tmAux, p, stream);

@@ -106,31 +106,39 @@ __device__ __forceinline__ int map_row(const mca_pack_desc& d, int r) {
   return d.dst_row0 + (v / 64) * 128 + gate * 64 + (v % 64);
 }
 
+// one warp per source row (no per-element division; loads coalesced along the row), grid.y = descriptor
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ arena,
                     const mca_pack_desc* __restrict__ descs) {
   const mca_pack_desc d = descs[blockIdx.y];
-  const long long n = static_cast<long long>(d.rows) * d.cols;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / d.cols), c = static_cast<int>(i % d.cols);
-    arena[d.dst_off + static_cast<long long>(map_row(d, r)) * d.dst_ld + c] =
-        __float2bfloat16(params[d.src_off + i] * d.scale);
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < d.rows; r += gridDim.x * 8) {
+    const float* src = params + d.src_off + static_cast<long long>(r) * d.cols;
+    __nv_bfloat16* dst = arena + d.dst_off + static_cast<long long>(map_row(d, r)) * d.dst_ld;
+    for (int c = lane; c < d.cols; c += 32) dst[c] = __float2bfloat16(src[c] * d.scale);
   }
 }
 
+// grads[row] = scale * sum over the n_splits slabs (warp per row, four independent row segments in flight per lane)
 __global__ void __launch_bounds__(256)
 unpack_grads_kernel(float* __restrict__ grads, const float* __restrict__ partials,
                     const mca_pack_desc* __restrict__ descs) {
   const mca_pack_desc d = descs[blockIdx.y];
-  const long long n = static_cast<long long>(d.rows) * d.cols;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / d.cols), c = static_cast<int>(i % d.cols);
-    const float* p = partials + d.dst_off + static_cast<long long>(map_row(d, r)) * d.dst_ld + c;
-    float acc = 0.f;
-    for (int z = 0; z < d.n_splits; ++z) acc += p[static_cast<long long>(z) * d.split_stride];
-    grads[d.src_off + i] = acc * d.scale;
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < d.rows; r += gridDim.x * 8) {
+    float* dst = grads + d.src_off + static_cast<long long>(r) * d.cols;
+    const float* p = partials + d.dst_off + static_cast<long long>(map_row(d, r)) * d.dst_ld;
+    for (int c0 = lane; c0 < d.cols; c0 += 128) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int z = 0; z < d.n_splits; ++z) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c0 + 32 * u < d.cols) acc[u] += p[static_cast<long long>(z) * d.split_stride + c0 + 32 * u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0 + 32 * u < d.cols) dst[c0 + 32 * u] = acc[u] * d.scale;
+    }
   }
 }
 
@@ -207,7 +215,7 @@ extern "C" int mca_build_offsets(const void* const* masks_host, const int* elem_
 extern "C" int mca_pack_weights(const float* params, void* arena_bf16, const mca_pack_desc* descs_dev, int n_desc,
                                 void* stream) {
   if (n_desc <= 0) return MCA_ERR_SHAPE;
-  dim3 grid(64, n_desc);
+  dim3 grid(48, n_desc);
   pack_weights_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       params, reinterpret_cast<__nv_bfloat16*>(arena_bf16), descs_dev);
   return check_launch();
@@ -216,7 +224,7 @@ extern "C" int mca_pack_weights(const float* params, void* arena_bf16, const mca
 extern "C" int mca_unpack_grads(float* grads, const float* partials, const mca_pack_desc* descs_dev, int n_desc,
                                 void* stream) {
   if (n_desc <= 0) return MCA_ERR_SHAPE;
-  dim3 grid(64, n_desc);
+  dim3 grid(48, n_desc);
   unpack_grads_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(grads, partials, descs_dev);
   return check_launch();
 }

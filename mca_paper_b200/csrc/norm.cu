@@ -267,37 +267,71 @@ lnw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
   }
 }
 
+// Column reductions over token rows.  Block = 128 rows x 128 columns: thread (cx = t % 32, ry = t / 32) walks rows
+// ry, ry + 8, ... for four 32-column groups (every warp load is one coalesced 128-byte line), the eight row groups are
+// combined in shared memory and one atomicAdd per column leaves the block.
+constexpr int CR_ROWS = 128, CR_COLS = 128;
+
 // parameter gradients of the input LayerNorm: dw[c] += sum_r dy[r,c]*xhat[r,c], db[c] += sum_r dy[r,c]
 __global__ void __launch_bounds__(256)
 lnw_param_bwd_kernel(const float* __restrict__ dy, int ld_dy, const float* __restrict__ x, const float2* __restrict__ stats,
                      const uint8_t* __restrict__ pad, float* __restrict__ dw, float* __restrict__ db, int width,
-                     long long rows, int rows_per_block) {
-  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
-  const long long r1 = min(rows, r0 + rows_per_block);
-  for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    float aw = 0.f, ab = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-      if (pad != nullptr && pad[r] != 0) continue;
-      const float2 st = stats[r];
-      const float d = dy[r * ld_dy + c];
-      aw += d * (x[r * width + c] - st.x) * st.y;
-      ab += d;
+                     long long rows) {
+  __shared__ float sw[8][CR_COLS], sb[8][CR_COLS];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const long long r0 = static_cast<long long>(blockIdx.x) * CR_ROWS;
+  const long long r1 = min(rows, r0 + CR_ROWS);
+  const int c0 = blockIdx.y * CR_COLS;
+  float aw[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = r0 + ry; r < r1; r += 8) {
+    if (pad != nullptr && pad[r] != 0) continue;
+    const float2 st = stats[r];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c = c0 + g * 32 + cx;
+      if (c < width) {
+        const float d = dy[r * ld_dy + c];
+        aw[g] += d * (x[r * width + c] - st.x) * st.y;
+        ab[g] += d;
+      }
     }
-    atomicAdd(dw + c, aw);
-    atomicAdd(db + c, ab);
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) sw[ry][g * 32 + cx] = aw[g], sb[ry][g * 32 + cx] = ab[g];
+  __syncthreads();
+  if (threadIdx.x < CR_COLS && c0 + threadIdx.x < width) {
+    float tw = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tw += sw[i][threadIdx.x], tb += sb[i][threadIdx.x];
+    atomicAdd(dw + c0 + threadIdx.x, tw);
+    atomicAdd(db + c0 + threadIdx.x, tb);
   }
 }
 
 // column sums: out[c] += sum_r a[r, c]  (bias gradients)
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ a, int ld, float* __restrict__ out, int width, long long rows,
-              int rows_per_block) {
-  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
-  const long long r1 = min(rows, r0 + rows_per_block);
-  for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    float acc = 0.f;
-    for (long long r = r0; r < r1; ++r) acc += a[r * ld + c];
-    atomicAdd(out + c, acc);
+colsum_kernel(const float* __restrict__ a, int ld, float* __restrict__ out, int width, long long rows) {
+  __shared__ float ss[8][CR_COLS];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const long long r0 = static_cast<long long>(blockIdx.x) * CR_ROWS;
+  const long long r1 = min(rows, r0 + CR_ROWS);
+  const int c0 = blockIdx.y * CR_COLS;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = r0 + ry; r < r1; r += 8) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c = c0 + g * 32 + cx;
+      if (c < width) acc[g] += a[r * ld + c];
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) ss[ry][g * 32 + cx] = acc[g];
+  __syncthreads();
+  if (threadIdx.x < CR_COLS && c0 + threadIdx.x < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += ss[i][threadIdx.x];
+    atomicAdd(out + c0 + threadIdx.x, t);
   }
 }
 
@@ -361,17 +395,15 @@ extern "C" int mca_layernorm_in_param_bwd(const float* dy, int ld_dy, const floa
                                           const uint8_t* pad, float* dw, float* db, int width, long long rows,
                                           void* stream) {
   if (rows <= 0 || width <= 0) return MCA_ERR_SHAPE;
-  const int rpb = 64;
-  const unsigned grid = static_cast<unsigned>((rows + rpb - 1) / rpb);
+  dim3 grid(static_cast<unsigned>((rows + CR_ROWS - 1) / CR_ROWS), (width + CR_COLS - 1) / CR_COLS);
   lnw_param_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, x, reinterpret_cast<const float2*>(stats), pad, dw, db, width, rows, rpb);
+      dy, ld_dy, x, reinterpret_cast<const float2*>(stats), pad, dw, db, width, rows);
   return check_launch();
 }
 
 extern "C" int mca_colsum(const float* a, int ld, float* out, int width, long long rows, void* stream) {
   if (rows <= 0 || width <= 0) return MCA_ERR_SHAPE;
-  const int rpb = 64;
-  const unsigned grid = static_cast<unsigned>((rows + rpb - 1) / rpb);
-  colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, ld, out, width, rows, rpb);
+  dim3 grid(static_cast<unsigned>((rows + CR_ROWS - 1) / CR_ROWS), (width + CR_COLS - 1) / CR_COLS);
+  colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, ld, out, width, rows);
   return check_launch();
 }

@@ -108,28 +108,79 @@ pool_fwd_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ 
         part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
 }
 
-// Same computation with one block per (sample, head): K and V rows are read ONCE for all R pooled rows (the kernel
-// above re-reads them per row).  Scores / probabilities of the whole [N, R] block live in shared memory.
-// grid = B*H, block 512; requires R <= 16 and N * round_up(R,4) * 4 bytes of shared memory.
-__global__ void __launch_bounds__(512)
-pool_fwd_bh_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ kv, const uint8_t* __restrict__ padding,
+// ------------------------------------------------------------------ cluster variants (R <= 16)
+// One thread-block CLUSTER of PC CTAs = one (sample, head); CTA c owns the keys [c*NC, (c+1)*NC).  K and V rows are
+// read once, the softmax statistics and the partial outputs are exchanged through distributed shared memory
+// (mapa + st.shared::cluster between cluster barriers), so the whole pooling forward (and backward) is one launch of
+// B*H*PC CTAs instead of B*H long-running blocks.  Scores / probabilities are kept [row][key] in shared memory so the
+// per-row passes are bank-conflict free.
+constexpr int PC = 8;
+constexpr int PR = 16;  // pooled rows supported by the cluster kernels
+
+__device__ __forceinline__ void cl_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cl_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// store into the same shared-memory variable of CTA `rank` of this cluster
+__device__ __forceinline__ void st_peer_f32(float* local_ptr, uint32_t rank, float v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// shared layout of both kernels (floats): q[16*64] g[16*64] a[16*NCP] b[16*NCP] xs0[PC*16] xs1[PC*16] part[4*16*64]
+// xpart[PC*16*64]
+__host__ __device__ inline size_t pool_cl_smem_floats(int NCP) {
+  return 2 * PR * DH + 2 * static_cast<size_t>(PR) * NCP + 2 * PC * PR + 4 * PR * DH + static_cast<size_t>(PC) * PR * DH;
+}
+
+__global__ void __cluster_dims__(PC, 1, 1) __launch_bounds__(256)
+pool_fwd_cl_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ kv, const uint8_t* __restrict__ padding,
                    const uint8_t* __restrict__ keygrp, const uint32_t* __restrict__ rowbits, float* __restrict__ probs,
-                   uint8_t* __restrict__ full_masked, float* __restrict__ out, int B, int H, int R, int N, int RS) {
-  extern __shared__ float sm[];
-  float* q = sm;              // [16][64]
-  float* sc = sm + 16 * DH;   // [N][RS]
-  const int h = blockIdx.x % H, b = blockIdx.x / H;
-  const int ld = 2 * H * DH;
+                   uint8_t* __restrict__ full_masked, float* __restrict__ out, int B, int H, int R, int N, int NC, int NCP) {
+  extern __shared__ __align__(16) float smc[];
+  float* sm = smc;
+  float* q = sm;                       // [16][64]
+  float* sc = q + 2 * PR * DH;         // [16][NCP] scores -> probabilities
+  float* xmax = sc + 2 * PR * NCP;     // [PC][16] row maxima of every CTA of the cluster
+  float* xsum = xmax + PC * PR;        // [PC][16] row sums
+  float* part = xsum + PC * PR;        // [4][16][64]
+  float* xpart = part + 4 * PR * DH;   // [PC][16][64] partial outputs gathered by rank 0
+  __shared__ uint32_t rb[PR];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 16 * DH; i += blockDim.x) q[i] = (i / DH) < R ? qp[(i / DH) * H * DH + h * DH + (i % DH)] : 0.f;
+  const uint32_t rank = cl_rank();
+  const int cid = blockIdx.x / PC;
+  const int h = cid % H, b = cid / H;
+  const int ld = 2 * H * DH;
+  const int j0 = static_cast<int>(rank) * NC;
+  const int nloc = max(0, min(NC, N - j0));
+  for (int i = tid; i < PR * DH; i += 256) q[i] = (i / DH) < R ? qp[(i / DH) * H * DH + h * DH + (i % DH)] : 0.f;
+  if (tid < PR) rb[tid] = tid < R ? rowbits[tid] : 0u;
   __syncthreads();
-  // ---- phase 1: masked scores
-  for (int j = tid; j < N; j += blockDim.x) {
+  // ---- phase 1: masked scores of this CTA's keys, thread = key
+  for (int jl = tid; jl < nloc; jl += 256) {
+    const int j = j0 + jl;
     float k[DH];
     load_row64(kv + (static_cast<long long>(b) * N + j) * ld + h * DH, k);
     const bool pad = padding[static_cast<long long>(b) * N + j] != 0;
     const uint32_t kg = keygrp[j];
-    for (int r = 0; r < R; ++r) {
+#pragma unroll 4
+    for (int r = 0; r < PR; ++r) {
       const float4* q4 = reinterpret_cast<const float4*>(q + r * DH);
       float s = 0.f;
 #pragma unroll
@@ -137,70 +188,244 @@ pool_fwd_bh_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict
         const float4 w = q4[c];
         s += w.x * k[4 * c] + w.y * k[4 * c + 1] + w.z * k[4 * c + 2] + w.w * k[4 * c + 3];
       }
-      const bool ok = !pad && ((rowbits[r] >> kg) & 1u);
-      sc[j * RS + r] = ok ? s : -CUDART_INF_F;
+      sc[r * NCP + jl] = (!pad && ((rb[r] >> kg) & 1u)) ? s : -CUDART_INF_F;
     }
-    for (int r = R; r < RS; ++r) sc[j * RS + r] = 0.f;
   }
   __syncthreads();
-  // ---- phase 2: softmax of row r by warp r (16 warps)
-  for (int r = warp; r < R; r += blockDim.x / 32) {
-    float mx = -CUDART_INF_F;
-    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sc[j * RS + r]);
+  // ---- phase 2: softmax statistics, warp w owns rows w and w + 8; exchanged across the cluster
+  float lmax[2], gmax[2];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float* prow = probs + (static_cast<long long>(b * H + h) * R + r) * N;
-    if (mx == -CUDART_INF_F) {
-      // every key masked: softmax of a constant row = 1/N over all N keys (padded and disallowed ones included)
-      const float u = 1.0f / static_cast<float>(N);
-      for (int j = lane; j < N; j += 32) sc[j * RS + r] = u, prow[j] = u;
-      if (lane == 0 && h == 0) full_masked[b * R + r] = 1;
-    } else {
-      float se = 0.f;
-      for (int j = lane; j < N; j += 32) {
-        const float s = sc[j * RS + r];
+  for (int i = 0; i < 2; ++i) {
+    const int r = warp + 8 * i;
+    float mx = -CUDART_INF_F;
+    for (int jl = lane; jl < nloc; jl += 32) mx = fmaxf(mx, sc[r * NCP + jl]);
+    lmax[i] = warp_max(mx);
+    if (lane < PC) st_peer_f32(&xmax[rank * PR + r], lane, lmax[i]);
+  }
+  cl_sync();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = warp + 8 * i;
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int p = 0; p < PC; ++p) mx = fmaxf(mx, xmax[p * PR + r]);
+    gmax[i] = mx;
+    float se = 0.f;
+    if (mx != -CUDART_INF_F) {
+      for (int jl = lane; jl < nloc; jl += 32) {
+        const float s = sc[r * NCP + jl];
         const float e = s == -CUDART_INF_F ? 0.f : expf(s - mx);
-        sc[j * RS + r] = e;
+        sc[r * NCP + jl] = e;
         se += e;
       }
+    }
+    se = warp_sum(se);
+    if (lane < PC) st_peer_f32(&xsum[rank * PR + r], lane, se);
+  }
+  cl_sync();
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-      const float inv = 1.0f / se;
-      for (int j = lane; j < N; j += 32) {
-        const float p = sc[j * RS + r] * inv;
-        sc[j * RS + r] = p;
-        prow[j] = p;
+  for (int i = 0; i < 2; ++i) {
+    const int r = warp + 8 * i;
+    if (r >= R) {  // rows beyond R only pad the block to 16: keep them finite
+      for (int jl = lane; jl < nloc; jl += 32) sc[r * NCP + jl] = 0.f;
+      continue;
+    }
+    float* prow = probs + (static_cast<long long>(b * H + h) * R + r) * N + j0;
+    if (gmax[i] == -CUDART_INF_F) {
+      // every key masked: softmax of a constant row = 1/N over all N keys (padded and disallowed ones included)
+      const float u = 1.0f / static_cast<float>(N);
+      for (int jl = lane; jl < nloc; jl += 32) sc[r * NCP + jl] = u, prow[jl] = u;
+    } else {
+      float tot = 0.f;
+#pragma unroll
+      for (int p = 0; p < PC; ++p) tot += xsum[p * PR + r];
+      const float inv = 1.0f / tot;
+      for (int jl = lane; jl < nloc; jl += 32) {
+        const float p = sc[r * NCP + jl] * inv;
+        sc[r * NCP + jl] = p;
+        prow[jl] = p;
       }
-      if (lane == 0 && h == 0) full_masked[b * R + r] = 0;
+    }
+    if (lane == 0 && h == 0 && rank == 0) full_masked[b * R + r] = gmax[i] == -CUDART_INF_F ? 1 : 0;
+  }
+  __syncthreads();
+  // ---- phase 3: partial out[r, c] = sum over this CTA's keys p[r, j] * V[j, c]; thread = (dim c, key group g of 4)
+  {
+    const int c = tid % DH, g = tid / DH;
+    float acc[PR];
+#pragma unroll
+    for (int r = 0; r < PR; ++r) acc[r] = 0.f;
+    const __nv_bfloat16* vcol = kv + (static_cast<long long>(b) * N + j0) * ld + H * DH + h * DH + c;
+    for (int jb = g; jb < nloc; jb += 32) {  // eight independent loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = jb + 4 * u < nloc ? __bfloat162float(vcol[static_cast<long long>(jb + 4 * u) * ld]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jl = jb + 4 * u < nloc ? jb + 4 * u : jb;  // v[u] = 0 beyond the chunk
+#pragma unroll
+        for (int r = 0; r < PR; ++r) acc[r] += sc[r * NCP + jl] * v[u];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < PR; ++r) part[(g * PR + r) * DH + c] = acc[r];
+  }
+  __syncthreads();
+  for (int i = tid; i < PR * DH; i += 256) {
+    const float t = part[i] + part[PR * DH + i] + part[2 * PR * DH + i] + part[3 * PR * DH + i];
+    st_peer_f32(&xpart[rank * PR * DH + i], 0, t);
+  }
+  cl_sync();
+  if (rank == 0) {
+    for (int i = tid; i < R * DH; i += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int p = 0; p < PC; ++p) t += xpart[p * PR * DH + i];
+      out[(static_cast<long long>(b) * R + i / DH) * H * DH + h * DH + (i % DH)] = t;
+    }
+  }
+}
+
+// Backward of the above in one launch: dP = g V^T, dS = P (dP - rowsum(P dP)) (zero for fully masked rows),
+// dK = dS^T q, dV = P^T g (bf16 rows of dkv), dqp += dS K (cluster-reduced, then one atomicAdd per output and sample).
+__global__ void __cluster_dims__(PC, 1, 1) __launch_bounds__(256)
+pool_bwd_cl_kernel(const float* __restrict__ dout, const float* __restrict__ qp, const __nv_bfloat16* __restrict__ kv,
+                   const float* __restrict__ probs, const uint8_t* __restrict__ full_masked,
+                   __nv_bfloat16* __restrict__ dkv, float* __restrict__ dqp, int B, int H, int R, int N, int NC, int NCP) {
+  extern __shared__ __align__(16) float smc[];
+  float* sm = smc;
+  float* q = sm;                        // [16][64]
+  float* g = q + PR * DH;               // [16][64]
+  float* ps = g + PR * DH;              // [16][NCP] probabilities
+  float* ds = ps + PR * NCP;            // [16][NCP] dP, then dS
+  float* xds = ds + PR * NCP;           // [PC][16] partial row sums of P dP
+  float* part = xds + 2 * PC * PR;      // [4][16][64]
+  float* xpart = part + 4 * PR * DH;    // [PC][16][64]
+  __shared__ uint8_t fm[PR];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cl_rank();
+  const int cid = blockIdx.x / PC;
+  const int h = cid % H, b = cid / H;
+  const int ld = 2 * H * DH;
+  const int j0 = static_cast<int>(rank) * NC;
+  const int nloc = max(0, min(NC, N - j0));
+  for (int i = tid; i < PR * DH; i += 256) {
+    const int r = i / DH, c = i % DH;
+    q[i] = r < R ? qp[r * H * DH + h * DH + c] : 0.f;
+    g[i] = r < R ? dout[(static_cast<long long>(b) * R + r) * H * DH + h * DH + c] : 0.f;
+  }
+  if (tid < PR) fm[tid] = tid < R ? full_masked[b * R + tid] : 1;
+  __syncthreads();
+  // ---- dP[r, j] = g[r] . V[j], thread = key
+  for (int jl = tid; jl < nloc; jl += 256) {
+    const int j = j0 + jl;
+    float v[DH];
+    load_row64(kv + (static_cast<long long>(b) * N + j) * ld + H * DH + h * DH, v);
+#pragma unroll 4
+    for (int r = 0; r < PR; ++r) {
+      const float4* g4 = reinterpret_cast<const float4*>(g + r * DH);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) {
+        const float4 w = g4[c];
+        s += w.x * v[4 * c] + w.y * v[4 * c + 1] + w.z * v[4 * c + 2] + w.w * v[4 * c + 3];
+      }
+      ds[r * NCP + jl] = s;
+      ps[r * NCP + jl] = r < R ? probs[(static_cast<long long>(b * H + h) * R + r) * N + j] : 0.f;
     }
   }
   __syncthreads();
-  // ---- phase 3: out[r, c] = sum_j p[r, j] * V[j, c]; thread = (dim c, key group g of 8)
-  const int c = tid % DH, g = tid / DH;
-  float acc[16];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) acc[r] = 0.f;
-  for (int j = g; j < N; j += 8) {
-    const float v = __bfloat162float(kv[(static_cast<long long>(b) * N + j) * ld + H * DH + h * DH + c]);
-    const float4* pj = reinterpret_cast<const float4*>(sc + j * RS);
-#pragma unroll
-    for (int r4 = 0; r4 < 4; ++r4)
-      if (r4 * 4 < R) {  // rows beyond R inside the last group of four hold padding that is never written out
-        const float4 p4 = pj[r4];
-        acc[4 * r4] += p4.x * v, acc[4 * r4 + 1] += p4.y * v, acc[4 * r4 + 2] += p4.z * v, acc[4 * r4 + 3] += p4.w * v;
-      }
+  for (int i = 0; i < 2; ++i) {
+    const int r = warp + 8 * i;
+    float s = 0.f;
+    for (int jl = lane; jl < nloc; jl += 32) s += ps[r * NCP + jl] * ds[r * NCP + jl];
+    s = warp_sum(s);
+    if (lane < PC) st_peer_f32(&xds[rank * PR + r], lane, s);
   }
-  __syncthreads();  // everyone is done reading sc: reuse it for the cross-group reduction [8][16][64]
-  float* part = sc;
+  cl_sync();
 #pragma unroll
-  for (int r = 0; r < 16; ++r) part[(g * 16 + r) * DH + c] = acc[r];
+  for (int i = 0; i < 2; ++i) {
+    const int r = warp + 8 * i;
+    float tot = 0.f;
+#pragma unroll
+    for (int p = 0; p < PC; ++p) tot += xds[p * PR + r];
+    const bool dead = fm[r] != 0;
+    for (int jl = lane; jl < nloc; jl += 32)
+      ds[r * NCP + jl] = dead ? 0.f : ps[r * NCP + jl] * (ds[r * NCP + jl] - tot);
+  }
   __syncthreads();
-  for (int i = tid; i < R * DH; i += blockDim.x) {
-    const int r = i / DH, cc = i % DH;
-    float t = 0.f;
+  // ---- dK / dV rows: thread = (key jl = t % 64 of a 64-key pass, 16-wide dim group t / 64)
+  {
+    const int c0 = (tid / 64) * 16;
+    for (int jb = 0; jb < nloc; jb += 64) {
+      const int jl = jb + (tid % 64);
+      if (jl < nloc) {
+        float ak[16], av[16];
 #pragma unroll
-    for (int gg = 0; gg < 8; ++gg) t += part[(gg * 16 + r) * DH + cc];
-    out[(static_cast<long long>(b) * R + r) * H * DH + h * DH + cc] = t;
+        for (int i = 0; i < 16; ++i) ak[i] = 0.f, av[i] = 0.f;
+#pragma unroll 2
+        for (int r = 0; r < PR; ++r) {
+          const float s = ds[r * NCP + jl], p = ps[r * NCP + jl];
+          const float4* q4 = reinterpret_cast<const float4*>(q + r * DH + c0);
+          const float4* g4 = reinterpret_cast<const float4*>(g + r * DH + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 qq = q4[i], gg = g4[i];
+            ak[4 * i] += s * qq.x, ak[4 * i + 1] += s * qq.y, ak[4 * i + 2] += s * qq.z, ak[4 * i + 3] += s * qq.w;
+            av[4 * i] += p * gg.x, av[4 * i + 1] += p * gg.y, av[4 * i + 2] += p * gg.z, av[4 * i + 3] += p * gg.w;
+          }
+        }
+        __nv_bfloat16* ok = dkv + (static_cast<long long>(b) * N + j0 + jl) * ld + h * DH + c0;
+        __nv_bfloat16* ov = ok + H * DH;
+        uint4 w0, w1;
+        w0.x = pack_bf16x2(ak[0], ak[1]), w0.y = pack_bf16x2(ak[2], ak[3]), w0.z = pack_bf16x2(ak[4], ak[5]);
+        w0.w = pack_bf16x2(ak[6], ak[7]);
+        w1.x = pack_bf16x2(ak[8], ak[9]), w1.y = pack_bf16x2(ak[10], ak[11]), w1.z = pack_bf16x2(ak[12], ak[13]);
+        w1.w = pack_bf16x2(ak[14], ak[15]);
+        reinterpret_cast<uint4*>(ok)[0] = w0, reinterpret_cast<uint4*>(ok)[1] = w1;
+        w0.x = pack_bf16x2(av[0], av[1]), w0.y = pack_bf16x2(av[2], av[3]), w0.z = pack_bf16x2(av[4], av[5]);
+        w0.w = pack_bf16x2(av[6], av[7]);
+        w1.x = pack_bf16x2(av[8], av[9]), w1.y = pack_bf16x2(av[10], av[11]), w1.z = pack_bf16x2(av[12], av[13]);
+        w1.w = pack_bf16x2(av[14], av[15]);
+        reinterpret_cast<uint4*>(ov)[0] = w0, reinterpret_cast<uint4*>(ov)[1] = w1;
+      }
+    }
+  }
+  // ---- dqp partial[r, c] = sum over this CTA's keys dS[r, j] * K[j, c]; thread = (dim c, key group of 4)
+  {
+    const int c = tid % DH, gq = tid / DH;
+    float acc[PR];
+#pragma unroll
+    for (int r = 0; r < PR; ++r) acc[r] = 0.f;
+    const __nv_bfloat16* kcol = kv + (static_cast<long long>(b) * N + j0) * ld + h * DH + c;
+    for (int jb = gq; jb < nloc; jb += 32) {  // eight independent loads in flight per thread
+      float kx[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) kx[u] = jb + 4 * u < nloc ? __bfloat162float(kcol[static_cast<long long>(jb + 4 * u) * ld]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jl = jb + 4 * u < nloc ? jb + 4 * u : jb;  // kx[u] = 0 beyond the chunk
+#pragma unroll
+        for (int r = 0; r < PR; ++r) acc[r] += ds[r * NCP + jl] * kx[u];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < PR; ++r) part[(gq * PR + r) * DH + c] = acc[r];
+  }
+  __syncthreads();
+  for (int i = tid; i < PR * DH; i += 256) {
+    const float t = part[i] + part[PR * DH + i] + part[2 * PR * DH + i] + part[3 * PR * DH + i];
+    st_peer_f32(&xpart[rank * PR * DH + i], 0, t);
+  }
+  cl_sync();
+  if (rank == 0) {
+    for (int i = tid; i < R * DH; i += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int p = 0; p < PC; ++p) t += xpart[p * PR * DH + i];
+      if (t != 0.f) atomicAdd(dqp + (i / DH) * H * DH + h * DH + (i % DH), t);
+    }
   }
 }
 
@@ -313,25 +538,33 @@ pool_bwd_kv_kernel(const float* __restrict__ ds, const float* __restrict__ probs
 }
 
 // ---- small fp32 GEMM: C[m,n] = alpha * sum_k A(m,k) B(n,k) (+ C if accumulate) (+ add[m % add_rows, n]); arbitrary
-// strides.  32x32 output tile per block (these problems have at most a few hundred rows: small tiles keep every SM
-// busy), 2x2 outputs per thread, 32-wide k steps staged through shared memory.
+// strides.  32x32 output tile per block, 2x2 outputs per thread, 32-wide k steps staged through shared memory.  These
+// problems have a few hundred rows at most and are pure latency, so the k range is split over a thread-block cluster
+// (1,1,KS): every CTA reduces its k slice, ships its partial tile to CTA 0 through distributed shared memory and CTA 0
+// adds the slices in a fixed order (deterministic) before the epilogue.
+constexpr int SG_MAX_KS = 8;
+
 __global__ void __launch_bounds__(256)
 small_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm,
                   long long sbn, long long sbk, float* __restrict__ C, long long ldc, const float* __restrict__ add,
-                  long long ldadd, int add_rows, int M, int N, int K, float alpha, int accumulate) {
+                  long long ldadd, int add_rows, int M, int N, int K, float alpha, int accumulate, int k_per) {
   __shared__ float As[32][33], Bs[32][33];  // [k][row]
+  __shared__ float xacc[SG_MAX_KS][32 * 32];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int KS = gridDim.z;
+  const uint32_t rank = blockIdx.z;
+  const int kbeg = static_cast<int>(rank) * k_per, kend = min(K, kbeg + k_per);
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  for (int k0 = kbeg; k0 < kend; k0 += 32) {
     // element e -> (row = e / 32, k = e % 32) when k is the fast stride, otherwise (k = e / 32, row = e % 32), so the
     // global reads stay coalesced for either layout
     for (int e = threadIdx.x; e < 32 * 32; e += 256) {
       int ra, ka, rb, kb;
       if (sak == 1) ra = e / 32, ka = e % 32; else ka = e / 32, ra = e % 32;
       if (sbk == 1) rb = e / 32, kb = e % 32; else kb = e / 32, rb = e % 32;
-      As[ka][ra] = (m0 + ra < M && k0 + ka < K) ? A[(m0 + ra) * sam + (k0 + ka) * sak] : 0.f;
-      Bs[kb][rb] = (n0 + rb < N && k0 + kb < K) ? Bm[(n0 + rb) * sbn + (k0 + kb) * sbk] : 0.f;
+      As[ka][ra] = (m0 + ra < M && k0 + ka < kend) ? A[(m0 + ra) * sam + (k0 + ka) * sak] : 0.f;
+      Bs[kb][rb] = (n0 + rb < N && k0 + kb < kend) ? Bm[(n0 + rb) * sbn + (k0 + kb) * sbk] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -340,6 +573,22 @@ small_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, con
       acc[0][0] += a0 * b0, acc[0][1] += a0 * b1, acc[1][0] += a1 * b0, acc[1][1] += a1 * b1;
     }
     __syncthreads();
+  }
+  if (KS > 1) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) st_peer_f32(&xacc[rank][(ty * 2 + i) * 32 + tx * 2 + j], 0, acc[i][j]);
+    cl_sync();
+    if (rank != 0) return;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float t = 0.f;
+        for (int z = 0; z < KS; ++z) t += xacc[z][(ty * 2 + i) * 32 + tx * 2 + j];
+        acc[i][j] = t;
+      }
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -361,27 +610,36 @@ small_gemm_kernel(const float* __restrict__ A, long long sam, long long sak, con
 
 using namespace mca;
 
+// cluster kernels: R <= 16 and the [16][N/PC] score block of one CTA within shared memory
+static bool pool_cluster_geometry(int R, int N, int* NC, int* NCP, size_t* bytes) {
+  *NC = (N + PC - 1) / PC;
+  *NCP = (*NC + 3) & ~3;
+  *bytes = pool_cl_smem_floats(*NCP) * sizeof(float);
+  return R <= PR && *bytes <= 200 * 1024;
+}
+
 extern "C" int mca_pool_attn_fwd(const float* qp, const void* kv, const uint8_t* padding, const uint8_t* keygrp,
                                  const uint32_t* rowbits, float* probs, uint8_t* full_masked, float* out, int B,
                                  int H, int R, int N, void* stream) {
   if (B <= 0 || R <= 0 || N <= 0 || N * 4 > 200 * 1024) return MCA_ERR_SHAPE;
+  int NC, NCP;
+  size_t bytes;
+  if (pool_cluster_geometry(R, N, &NC, &NCP, &bytes)) {
+    static bool attr2 = false;
+    if (!attr2) {
+      if (cudaFuncSetAttribute(pool_fwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return MCA_ERR_CUDA;
+      attr2 = true;
+    }
+    pool_fwd_cl_kernel<<<B * H * PC, 256, bytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+        qp, reinterpret_cast<const __nv_bfloat16*>(kv), padding, keygrp, rowbits, probs, full_masked, out, B, H, R, N, NC,
+        NCP);
+    return check_launch();
+  }
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(pool_bwd_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
-  }
-  const int RS = (R + 3) / 4 * 4;
-  const size_t need = (16 * DH + static_cast<size_t>(N) * RS) * sizeof(float);
-  if (R <= 16 && need <= 200 * 1024 && static_cast<size_t>(N) * RS >= 8 * 16 * DH) {
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(pool_fwd_bh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr2 = true;
-    }
-    pool_fwd_bh_kernel<<<B * H, 512, need, reinterpret_cast<cudaStream_t>(stream)>>>(
-        qp, reinterpret_cast<const __nv_bfloat16*>(kv), padding, keygrp, rowbits, probs, full_masked, out, B, H, R, N, RS);
-    return check_launch();
   }
   pool_fwd_kernel<<<B * H * R, 256, N * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       qp, reinterpret_cast<const __nv_bfloat16*>(kv), padding, keygrp, rowbits, probs, full_masked, out, B, H, R, N);
@@ -393,16 +651,29 @@ extern "C" int mca_pool_attn_bwd(const float* dout, const float* qp, const void*
                                  int R, int N, void* stream_) {
   if (B <= 0 || R <= 0 || N <= 0 || N * 4 > 200 * 1024) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const __nv_bfloat16* kvb = reinterpret_cast<const __nv_bfloat16*>(kv);
+  if (cudaMemsetAsync(dqp, 0, static_cast<size_t>(R) * H * DH * sizeof(float), stream) != cudaSuccess) return MCA_ERR_CUDA;
+  int NC, NCP;
+  size_t bytes;
+  if (pool_cluster_geometry(R, N, &NC, &NCP, &bytes)) {
+    static bool attr2 = false;
+    if (!attr2) {
+      if (cudaFuncSetAttribute(pool_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return MCA_ERR_CUDA;
+      attr2 = true;
+    }
+    pool_bwd_cl_kernel<<<B * H * PC, 256, bytes, stream>>>(dout, qp, kvb, probs, full_masked,
+                                                           reinterpret_cast<__nv_bfloat16*>(dkv), dqp, B, H, R, N, NC, NCP);
+    return check_launch();
+  }
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(pool_bwd_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  const __nv_bfloat16* kvb = reinterpret_cast<const __nv_bfloat16*>(kv);
   pool_bwd_scores_kernel<<<B * H * R, 256, N * sizeof(float), stream>>>(dout, kvb, probs, full_masked, ds_scratch, B, H,
                                                                         R, N);
   dim3 g2((N + 63) / 64, H, B);
-  if (cudaMemsetAsync(dqp, 0, static_cast<size_t>(R) * H * DH * sizeof(float), stream) != cudaSuccess) return MCA_ERR_CUDA;
   const size_t sm2 = (3 * static_cast<size_t>(R) * DH + 64 * 65) * sizeof(float);
   if (sm2 > 48 * 1024) return MCA_ERR_SHAPE;  // R <= 42
   pool_bwd_kv_kernel<<<g2, 256, sm2, stream>>>(ds_scratch, probs, qp, dout, kvb, reinterpret_cast<__nv_bfloat16*>(dkv),
@@ -414,8 +685,23 @@ extern "C" int mca_small_gemm_f32(const float* A, long long sam, long long sak, 
                                   long long sbk, float* C, long long ldc, const float* add, long long ldadd,
                                   int add_rows, int M, int N, int K, float alpha, int accumulate, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return MCA_ERR_SHAPE;
-  dim3 grid((N + 31) / 32, (M + 31) / 32);
-  small_gemm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, add,
-                                                                             ldadd, add_rows, M, N, K, alpha, accumulate);
+  // split k over a cluster until the grid covers the machine (each CTA keeps at least one 32-wide k step)
+  const int tiles = ((N + 31) / 32) * ((M + 31) / 32);
+  int ks = 1;
+  while (ks < SG_MAX_KS && tiles * ks < 2 * num_sms() && K / (2 * ks) >= 32) ks *= 2;
+  const int k_per = ((K + ks - 1) / ks + 31) / 32 * 32;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((N + 31) / 32, (M + 31) / 32, ks);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = ks;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, small_gemm_kernel, A, sam, sak, Bm, sbn, sbk, C, ldc, add, ldadd, add_rows, M, N, K, alpha,
+                         accumulate, k_per) != cudaSuccess)
+    return MCA_ERR_CUDA;
   return check_launch();
 }

@@ -113,7 +113,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ weight layouts
     def _build_pack_descs(self, dev):
-        """bf16 operand arena (kernel layouts) and fp32 split-K partial arena for weight gradients."""
+        """bf16 operand arena (kernel layouts) and the fp32 weight-gradient arena: ONE kernel-layout slab per matrix
+        that every k-split of the dW GEMM reduce-adds into (MCA_EPI_F32_ACC); trunk_backward zeroes it first."""
         descs = np.zeros(0, dtype=ops.PACK_DESC_DTYPE)
         rows: List[tuple] = []
         self.w = {}    # name -> (arena offset, rows, ld)
@@ -128,9 +129,9 @@ class Engine:
             self.w[key] = (a_off, r, c)
             self.gw[key] = (g_off, splits, r * c)
             for (pname, prow, pcol, row0, mode, half, scale) in parts:
-                rows.append((self.offs[pname], a_off, prow, pcol, c, row0, mode, half, scale, g_off, splits, r * c))
+                rows.append((self.offs[pname], a_off, prow, pcol, c, row0, mode, half, scale, g_off, 1, r * c))
             a_off += _round_up(r * c, 512)
-            g_off += _round_up(splits * r * c, 512)
+            g_off += _round_up(r * c, 512)
 
         I, IP, M = self.I, self.IP, self.M
         for l in range(self.depth):
@@ -167,10 +168,10 @@ class Engine:
         o, r, c = self.w[key]
         return self.arena[o:o + r * c].view(r, c)
 
-    def GW(self, key):  # fp32 split-K partial slabs
+    def GW(self, key):  # fp32 kernel-layout gradient slab + the number of k-splits that reduce into it
         o, s, slab = self.gw[key]
         r, c = self.w[key][1], self.w[key][2]
-        return self.garena[o:o + s * slab].view(s, r, c), s
+        return self.garena[o:o + slab].view(1, r, c), s
 
     def pack_weights(self):
         call("mca_pack_weights", P(self.flat), P(self.arena), P(self.pack_descs), self.n_desc, S())
@@ -396,14 +397,16 @@ class Engine:
         return g["dpooled"]
 
     def _dw(self, key, dY, X, rows_w, cols_w, tokens):
-        """dW[rows_w, cols_w] = dY^T X over `tokens` rows, both operands consumed MN-major, split-K partial slabs."""
+        """dW[rows_w, cols_w] += dY^T X over `tokens` rows, both operands consumed MN-major; the k-splits reduce-add
+        into one slab (zeroed at the start of trunk_backward)."""
         part, splits = self.GW(key)
-        ops.gemm(dY, 1, X, 1, rows_w, cols_w, tokens, _lib.EPI_F32, part, ld0=cols_w, k_splits=splits)
+        ops.gemm(dY, 1, X, 1, rows_w, cols_w, tokens, _lib.EPI_F32_ACC, part, ld0=cols_w, k_splits=splits)
 
     def trunk_backward(self, dpooled):
         """Reverse of trunk_forward; parameter gradients land in self.flat_grad (state_dict layout)."""
         ws, pl, M, IP, B, R, H, N = self.ws, self.plan, self.M, self.IP, self.B, self.R, self.H, self.N
         rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
+        self.garena.zero_()  # every dW GEMM reduce-adds its k-splits into this arena
         dp2 = dpooled.reshape(B * R, D)
         po2 = ws["po"].view(B * R, D)
         # pooled = po Wo^T + rt
