@@ -35,12 +35,13 @@ constexpr int AB_DS = AB_T * AB_T * 2;     // 32 KB bf16 dS tile, stored [key][q
 constexpr int AB_DQ = AB_T * AB_DH * 4;    // 32 KB fp32 [128, 64]
 constexpr int AB_QSTAGES = 3;
 constexpr int AB_MAX_ITERS = 64;  // query tiles attending one key tile
-// sK, sV, 3x(sQ, sdO), sdS (half 0 double buffered, half 1 single), sdQ; per-query staging and barriers are static
-// extra k-step operands (K-major, no swizzle: 8-row x 16-byte core matrices, 128 B between the two k chunks, 256 B
-// between 8-row groups): A rows for S^T [128 x 16], A rows for dP^T [128 x 16], B rows per query half [64 x 16] x 2
-constexpr int AB_EXT_A = AB_T * 32;
-constexpr int AB_EXT_B = 64 * 32;
-constexpr int AB_EXT = 2 * AB_EXT_A + 2 * AB_EXT_B;
+// sK, sV, 3x(sQ, sdO), sdS (half 0 double buffered, half 1 single), sdQ, extra k-step operands; barriers are static
+// extra k-step operands (K-major, no swizzle: 8-row x 16-byte core matrices).  Only the first 8-element k chunk of a
+// row carries data; the second chunk of EVERY operand is the same all-zero block (the descriptor's leading-dimension
+// offset points each tile at it), so a [128 x 16] operand costs 2 KB: A rows for S^T, A rows for dP^T, B rows of the
+// 128 queries of a tile (double buffered by tile parity), zero block.
+constexpr int AB_EXT_TILE = AB_T * 16;
+constexpr int AB_EXT = 5 * AB_EXT_TILE;
 constexpr int AB_SMEM = 2 * AB_TILE + 2 * AB_QSTAGES * AB_TILE + 3 * (AB_DS / 2) + AB_DQ + AB_EXT;
 constexpr float AB_MASKED = -60000.f;  // -lse of a query that must not see this key tile: exp2 underflows to 0
 constexpr float AB_LOG2E = 1.4426950408889634f;
@@ -84,17 +85,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sdS = sdO + AB_QSTAGES * AB_TILE;  // [half 0, buffer 0][half 0, buffer 1][half 1], 16 KB each
   uint8_t* sdQ = sdS + 3 * (AB_DS / 2);       // two 32-column fp32 boxes
   uint8_t* sAS = sdQ + AB_DQ;                 // extra k-step: A rows of the S^T product (ones in k = 0..2)
-  uint8_t* sAD = sAS + AB_EXT_A;              //               A rows of the dP^T product (ones in k = 3..5)
-  uint8_t* sBX = sAD + AB_EXT_A;              //               B rows [half][query]: -lse (k 0..2), -delta (k 3..5)
+  uint8_t* sAD = sAS + AB_EXT_TILE;           //               A rows of the dP^T product (ones in k = 3..5)
+  uint8_t* sBX = sAD + AB_EXT_TILE;           //               B rows [tile parity][query]: -lse (k 0..2), -delta (k 3..5)
+  uint8_t* sZ = sBX + 2 * AB_EXT_TILE;        //               the shared all-zero second k chunk
   __shared__ int2 s_qt[AB_MAX_ITERS];                 // (start, len) of every query tile this CTA visits
-  __shared__ __align__(16) uint32_t s_rb[2][2][64];   // allowed-key-group bits (mixed-group tiles only)
+  __shared__ __align__(16) uint32_t s_rb[2][3][64];   // allowed-key-group bits (mixed-group tiles only), by tile % 3
   __shared__ uint64_t bars[24];
   __shared__ uint32_t tmem_holder_s;
   uint64_t* kv_full = bars + 0;
   uint64_t* qdo_full = bars + 1;   // [AB_QSTAGES]
   uint64_t* qdo_empty = bars + 4;  // [AB_QSTAGES]
-  uint64_t* x_full = bars + 7;     // [2] per half: S^T / dP^T of the half are in TMEM
-  uint64_t* x_free = bars + 9;     // [2] per half: the compute warpgroup has copied them to registers
+  uint64_t* x_full = bars + 7;     // S^T / dP^T of the tile (both query halves, one N = 128 product each) are in TMEM
+  uint64_t* x_free = bars + 9;     // both compute warpgroups have copied them to registers and written the next B rows
   uint64_t* c_done = bars + 11;    // [2] per half: P^T / dS^T written (TMEM + smem)
   uint64_t* y_done = bars + 13;    // [2] per half: its dV / dK products retired, the shared P^T / dS^T columns are free
                                    // (one barrier per half: a waiter can then never be a whole phase ahead of it)
@@ -119,7 +121,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tma_prefetch_desc(&tm_dq);
     mbar_init(kv_full, 1);
     for (int s = 0; s < AB_QSTAGES; ++s) mbar_init(&qdo_full[s], 1), mbar_init(&qdo_empty[s], 1);
-    for (int s = 0; s < 2; ++s) mbar_init(&x_full[s], 1), mbar_init(&x_free[s], 128), mbar_init(&c_done[s], 128);
+    mbar_init(x_full, 1), mbar_init(x_free, 256);
+    for (int s = 0; s < 2; ++s) mbar_init(&c_done[s], 128);
     mbar_init(&y_done[0], 1), mbar_init(&y_done[1], 1);
     mbar_init(&z_full[0], 1), mbar_init(&z_full[1], 1);
     mbar_init(dq_free, 128);
@@ -132,20 +135,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const mca_attn_tile Q = a.q_tiles[a.qt_list[KT.kt_off + i].tile];
     s_qt[i] = make_int2(Q.start, Q.len);
   }
-  if (threadIdx.x < 256) {  // constant rows of the extra k-step (bf16 1.0 = 0x3F80); the second k chunk is all zero
-    const int row = threadIdx.x & 127, which = threadIdx.x >> 7;
-    uint8_t* dst = (which == 0 ? sAS : sAD) + (row >> 3) * 256 + (row & 7) * 16;
+  // constant rows of the extra k-step (bf16 1.0 = 0x3F80) and the zero block
+  for (int i = threadIdx.x; i < 3 * AB_T; i += AB_THREADS) {
+    const int row = i & 127, which = i >> 7;
+    uint8_t* dst = (which == 0 ? sAS : (which == 1 ? sAD : sZ)) + row * 16;
     *reinterpret_cast<uint4*>(dst) = which == 0 ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u)
-                                                : make_uint4(0u, 0x3F800000u, 0x3F803F80u, 0u);
-    *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
-    if (row < 64) *reinterpret_cast<uint4*>(sBX + which * AB_EXT_B + (row >> 3) * 256 + 128 + (row & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async_smem();
+                                   : (which == 1 ? make_uint4(0u, 0x3F800000u, 0x3F803F80u, 0u) : make_uint4(0u, 0u, 0u, 0u));
   }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  // columns: [0,128) S^T_0 | dP^T_0, [128,256) S^T_1 | dP^T_1, [256,320) P^T (32) | dS^T (32) of the half in flight,
+  // columns: [0,128) S^T (queries 0..127), [128,256) dP^T, [256,320) P^T (32) | dS^T (32) of the half in flight,
   //          [320,384) dV, [384,448) dK, [448,512) dQ
   const uint32_t tP = tmem_base + 256, tdV = tmem_base + 320, tdK = tmem_base + 384, tdQ = tmem_base + 448;
   if (threadIdx.x == 0) TRG(0);
@@ -194,7 +196,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     // tcgen05.mma costs one uniform add); one elected lane issues the MMAs and commits.  Independent accumulation
     // chains are interleaved (S^T with dP^T, dV with dK).
     if (n_iter > 0) {
-      constexpr uint32_t id_x = make_idesc_bf16(AB_T, 64, false, false);    // S^T, dP^T: K-major x K-major, N = 64
+      constexpr uint32_t id_x = make_idesc_bf16(AB_T, AB_T, false, false);  // S^T, dP^T: K-major x K-major, N = 128
       constexpr uint32_t id_y = make_idesc_bf16(AB_T, AB_DH, false, true);  // dV, dK: A from TMEM, B MN-major
       constexpr uint32_t id_z = make_idesc_bf16(AB_T, AB_DH, true, true);   // dQ: MN-major x MN-major
       const uint64_t dk_k = make_smem_desc_sw128(smem_u32(sK), 16, 1024);     // K as the K-major A operand of S^T
@@ -204,22 +206,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const uint64_t do_k0 = make_smem_desc_sw128(smem_u32(sdO), 16, 1024);
       const uint64_t dq_mn0 = make_smem_desc_sw128(smem_u32(sQ), 8192, 1024);
       const uint64_t do_mn0 = make_smem_desc_sw128(smem_u32(sdO), 8192, 1024);
-      const uint64_t d_as = make_smem_desc_nosw(smem_u32(sAS), 128, 256);
-      const uint64_t d_ad = make_smem_desc_nosw(smem_u32(sAD), 128, 256);
-      const uint64_t d_bx = make_smem_desc_nosw(smem_u32(sBX), 128, 256);
-      auto issue_x = [&](int t, int hf) {
-        const uint64_t off = static_cast<uint64_t>(((t % AB_QSTAGES) * AB_TILE + hf * 8192) >> 4);
-        const uint32_t reg = tmem_base + hf * 128;
-        const uint64_t bx = d_bx + static_cast<uint64_t>((hf * AB_EXT_B) >> 4);
+      // leading-dimension offset = distance to the shared zero chunk, stride 128 B between 8-row groups
+      const uint64_t d_as = make_smem_desc_nosw(smem_u32(sAS), 4 * AB_EXT_TILE, 128);
+      const uint64_t d_ad = make_smem_desc_nosw(smem_u32(sAD), 3 * AB_EXT_TILE, 128);
+      const uint64_t d_bx0 = make_smem_desc_nosw(smem_u32(sBX), 2 * AB_EXT_TILE, 128);
+      const uint64_t d_bx1 = make_smem_desc_nosw(smem_u32(sBX) + AB_EXT_TILE, AB_EXT_TILE, 128);
+      // S^T = K Q^T and dP^T = V dO^T for all 128 queries of the tile at once: the K / V rows (the A operands) are
+      // read from shared memory once per k-step instead of once per query half
+      auto issue_x = [&](int t) {
+        const uint64_t off = static_cast<uint64_t>(((t % AB_QSTAGES) * AB_TILE) >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < AB_DH / 16; ++k) {
-            umma_bf16(reg, dk_k + k * 2, dq_k0 + off + k * 2, id_x, k > 0 ? 1u : 0u);
-            umma_bf16(reg + 64, dv_k + k * 2, do_k0 + off + k * 2, id_x, k > 0 ? 1u : 0u);
+            umma_bf16(tmem_base, dk_k + k * 2, dq_k0 + off + k * 2, id_x, k > 0 ? 1u : 0u);
+            umma_bf16(tmem_base + 128, dv_k + k * 2, do_k0 + off + k * 2, id_x, k > 0 ? 1u : 0u);
           }
-          umma_bf16(reg, d_as, bx, id_x, 1u);        // S^T  -= lse_q
-          umma_bf16(reg + 64, d_ad, bx, id_x, 1u);   // dP^T -= delta_q
-          umma_commit(&x_full[hf]);
+          const uint64_t bx = (t & 1) ? d_bx1 : d_bx0;
+          umma_bf16(tmem_base, d_as, bx, id_x, 1u);        // S^T  -= lse_q
+          umma_bf16(tmem_base + 128, d_ad, bx, id_x, 1u);  // dP^T -= delta_q
+          umma_commit(x_full);
         }
         __syncwarp();
       };
@@ -242,22 +247,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       if (lane == 0) TRG(1);
       mbar_wait(&qdo_full[0], 0);
       if (lane == 0) TRG(2);
-      // x_free[h] phase n = "the B rows of tile n are written and S^T / dP^T of tile n-1 have been read"
-      mbar_wait(&x_free[0], 0);
+      // x_free phase n = "the B rows of tiles <= n + 1 are written and S^T / dP^T of tile n - 1 have been read"
+      mbar_wait(x_free, 0);
       tc_fence_after();
-      issue_x(0, 0);
-      mbar_wait(&x_free[1], 0);
-      tc_fence_after();
-      issue_x(0, 1);
+      issue_x(0);
       for (int t = 0; t < n_iter; ++t) {
         const uint32_t ph = t & 1;
         const bool more = t + 1 < n_iter;
         if (lane == 0) TR(2, t, 0);
         if (more) {
           mbar_wait(&qdo_full[(t + 1) % AB_QSTAGES], ((t + 1) / AB_QSTAGES) & 1);
-          mbar_wait(&x_free[0], ph ^ 1);  // S^T_0 / dP^T_0 of tile t are in registers: overwrite them right away
+          mbar_wait(x_free, ph ^ 1);  // S^T / dP^T of tile t are in registers: overwrite them right away
           tc_fence_after();
-          issue_x(t + 1, 0);
+          issue_x(t + 1);
         }
         if (lane == 0) TR(2, t, 1);
         mbar_wait(&c_done[0], ph);
@@ -265,11 +267,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tc_fence_after();
         issue_y(t, 0, false);
         if (lane == 0) TR(2, t, 3);
-        if (more) {
-          mbar_wait(&x_free[1], ph ^ 1);
-          tc_fence_after();
-          issue_x(t + 1, 1);
-        }
         if (lane == 0) TR(2, t, 4);
         mbar_wait(&c_done[1], ph);
         if (lane == 0) TR(2, t, 5);
@@ -299,7 +296,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int r = (warp & 3) * 32 + lane;  // key row = TMEM lane
     const int wt = threadIdx.x & 127;      // thread index inside the warpgroup
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t reg = tmem_base + hf * 128 + lane_sel;
+    const uint32_t reg = tmem_base + hf * 64 + lane_sel;  // S^T columns of this half; dP^T is 128 columns further
     const int kgrp = a.tile_grp[kt];
     const bool has_dead = cls == 1 || KT.len < AB_T;
     bool live = false;
@@ -325,12 +322,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         r_rb = a.rowbits[qi];
       }
     };
-    auto split3 = [](float v, uint32_t& h, uint32_t& m, uint32_t& l) {  // v = h + m + l in bf16 terms
-      const __nv_bfloat16 bh = __float2bfloat16_rn(v);
-      const float r1 = v - __bfloat162float(bh);
-      const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
-      const __nv_bfloat16 bl = __float2bfloat16_rn(r1 - __bfloat162float(bm));
-      h = __bfloat16_as_ushort(bh), m = __bfloat16_as_ushort(bm), l = __bfloat16_as_ushort(bl);
+    // v = h + m + l exactly: three 8-bit slices of the fp32 significand, each a bf16 (truncation, no cvt instructions)
+    auto split3 = [](float v, uint32_t& h, uint32_t& m, uint32_t& l) {
+      const uint32_t vh = __float_as_uint(v) & 0xFFFF0000u;
+      const float r1 = v - __uint_as_float(vh);
+      const uint32_t vm = __float_as_uint(r1) & 0xFFFF0000u;
+      const float r2 = r1 - __uint_as_float(vm);
+      h = vh >> 16, m = vm >> 16, l = __float_as_uint(r2) >> 16;
     };
     auto write_ext = [&](int t) {  // B row of this thread's query for tile t (from the registers loaded for t)
       if (wt < 64 && t < n_iter) {
@@ -340,14 +338,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         uint32_t lh, lm, ll, dh, dm, dl;
         split3(sees ? -r_lse : AB_MASKED, lh, lm, ll);
         split3(valid ? -r_dl : 0.f, dh, dm, dl);
-        *reinterpret_cast<uint4*>(sBX + hf * AB_EXT_B + (wt >> 3) * 256 + (wt & 7) * 16) =
+        const int q = hf * 64 + wt;  // row of the [128 x 16] B tile of this tile parity
+        *reinterpret_cast<uint4*>(sBX + (t & 1) * AB_EXT_TILE + q * 16) =
             make_uint4(lh | (lm << 16), ll | (dh << 16), dm | (dl << 16), 0u);
-        if (kgrp == 255) s_rb[hf][t & 1][wt] = rb;
+        if (kgrp == 255) s_rb[hf][t % 3][wt] = rb;
         fence_proxy_async_smem();
       }
     };
     auto drain_dq = [&](int tp) {  // dQ of tile tp: TMEM -> registers -> fp32 swizzled smem (the reduce warp ships it)
       mbar_wait(&z_full[tp & 1], (tp >> 1) & 1);
+      if (wt == 0) TR(hf, tp, 11);
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld32(tdQ + lane_sel, v0);
@@ -355,7 +355,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_free);
+      if (wt == 0) TR(hf, tp, 12);
       if (tp > 0) mbar_wait(sdq_free, (tp - 1) & 1);
+      if (wt == 0) TR(hf, tp, 13);
       uint8_t* rowp = sdQ + r * 128;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -368,28 +370,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     load_q(0);
     write_ext(0);
     load_q(1);
-    mbar_arrive(&x_free[hf]);  // phase 0: the B rows of tile 0 are in place
+    write_ext(1);
+    load_q(2);
+    mbar_arrive(x_free);  // phase 0: the B rows of tiles 0 and 1 are in place
     for (int t = 0; t < n_iter; ++t) {
       const uint32_t ph = t & 1;
       if (wt == 0) TR(hf, t, 0);
-      mbar_wait(&x_full[hf], ph);
+      mbar_wait(x_full, ph);
       if (wt == 0) TR(hf, t, 2);
       tc_fence_after();
       uint32_t sv[2][32], dv[2][32];
       tmem_ld32(reg, sv[0]);
       tmem_ld32(reg + 32, sv[1]);
-      tmem_ld32(reg + 64, dv[0]);
-      tmem_ld32(reg + 96, dv[1]);
-      // mixed-group key tiles read the queries' group bits from shared memory: everyone is done with the buffer that
-      // write_ext(t + 1) overwrites, and the bits of tile t (written one iteration ago) become visible
-      if (kgrp == 255) ab_bar_sync(1 + hf, 128);
-      write_ext(t + 1);  // X(t) has retired (x_full): its B rows may be replaced
-      load_q(t + 2);
+      tmem_ld32(reg + 128, dv[0]);
+      tmem_ld32(reg + 160, dv[1]);
       tmem_ld_wait();
       if (wt == 0) TR(hf, t, 3);
       tc_fence_before();
-      mbar_arrive(&x_free[hf]);  // the next tile's S^T / dP^T of this half may be issued now
-      const uint32_t* rbq = s_rb[hf][t & 1];
+      mbar_arrive(x_free);  // the next tile's S^T / dP^T may be issued once both warpgroups got here
+      // B rows of tile t + 2 go into the buffer X(t) has just finished with (x_full); X(t + 2) is only issued after
+      // this thread's arrival of iteration t + 1.  Mixed-group key tiles also keep the queries' group bits in shared
+      // memory (by tile % 3): the barrier makes sure nobody still reads the slot being replaced (tile t - 1) and
+      // publishes the bits written in earlier iterations.
+      if (kgrp == 255) ab_bar_sync(1 + hf, 128);
+      write_ext(t + 2);
+      load_q(t + 3);
+      if (wt == 0) TR(hf, t, 9);
+      const uint32_t* rbq = s_rb[hf][t % 3];
       // accumulators already hold S^T - lse[q] and dP^T - delta[q]:  P^T = exp2(log2e * .),  dS^T = P^T * (.)
 #pragma unroll
       for (int e = 0; e < 64; ++e) {

@@ -25,7 +25,7 @@ a = np.array(buf[:], dtype=np.int64)
 g = a[4 * 16 * 16:]
 t0 = g[0]
 print("global: setup_done=0 kv_full=%d q0_full=%d epi_wg0=%d epi_wg1=%d end_wg0=%d end_wg1=%d cta_end=%d" % tuple(int(x - t0) for x in g[1:8]))
-ev = a[:4 * 16 * 16].reshape(4, 16, 16)[:, :, :12]
+ev = a[:4 * 16 * 16].reshape(4, 16, 16)[:, :, :16]
 names = {0: "WG0", 1: "WG1", 2: "MMA"}
 for t in range(13):
     for role in (2, 0, 1):

@@ -8,7 +8,7 @@
 using namespace mca;
 
 // warps 0..nw-1 load (mode 0) or store (mode 1) `iters` x 4 x (32 lanes x 32 columns); warp 8 optionally issues MMAs
-__global__ void __launch_bounds__(288, 1) tmem_rate_kernel(int nw, int mode, int iters, int mma_iters, long long* out) {
+__global__ void __launch_bounds__(288, 1) tmem_rate_kernel(int nw, int mode, int iters, int mma_iters, int mma_ts, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t holder;
@@ -48,12 +48,19 @@ __global__ void __launch_bounds__(288, 1) tmem_rate_kernel(int nw, int mode, int
     if (lane == 0) tstart[warp] = t0, tend[warp] = t1;
   } else if (warp == 8 && mma_iters > 0) {
     const uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+    const uint32_t idesc_ts = make_idesc_bf16(128, 64, false, true);
     const uint64_t da = make_smem_desc_sw128(smem_u32(smem), 16, 1024), db = make_smem_desc_sw128(smem_u32(smem + 32768), 16, 1024);
+    const uint64_t dbm = make_smem_desc_sw128(smem_u32(smem + 32768), 8192, 1024);
     const long long t0 = clock64();
     for (int i = 0; i < mma_iters; i += 4) {
       if (elect_one()) {
+        if (mma_ts) {  // A operand from TMEM (the dV / dK / PV products of the attention kernels), B MN-major
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tm + 448, da + k * 2, db + k * 2, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tm + 448, tm + 384 + k * 8, dbm + k * 128, idesc_ts, 1u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + 448, da + k * 2, db + k * 2, idesc, 1u);
+        }
       }
       __syncwarp();
     }
@@ -84,12 +91,12 @@ int main() {
   printf("%-6s %-5s %-9s %12s %12s %14s\n", "mode", "warps", "mma", "cycles", "mma cycles", "B/cycle/SM");
   for (int mode = 0; mode < 2; ++mode)
     for (int nw : {1, 4, 8})
-      for (int mma : {0, 1}) {
+      for (int mma : {0, 1, 2}) {
         const int mma_iters = mma ? 16000 : 0;
-        tmem_rate_kernel<<<1, 288, 64 * 1024 + 1024>>>(nw, mode, iters, mma_iters, out);
+        tmem_rate_kernel<<<1, 288, 64 * 1024 + 1024>>>(nw, mode, iters, mma_iters, mma == 2, out);
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
         const double bytes = double(nw) * iters * 4 * 32 * 32 * 4;
-        printf("%-6s %-5d %-9s %12lld %12lld %14.1f\n", mode == 0 ? "ld" : "st", nw, mma ? "128x64x16" : "-", out[0], out[1],
+        printf("%-6s %-5d %-9s %12lld %12lld %14.1f\n", mode == 0 ? "ld" : "st", nw, mma == 0 ? "-" : (mma == 1 ? "SS 128x64" : "TS 128x64"), out[0], out[1],
                bytes / double(out[0]));
       }
   return 0;
