@@ -74,17 +74,18 @@ int main() {
   const int iters = 2048;
   const char* am[] = {"A smem K-major", "A smem MN-major", "A TMEM"};
   for (int n_acc : {1, 2})
-  for (int a_mode : {0, 2})
-      for (int n : {64, 128, 256}) {
-        if (n_acc * n > 448) continue;
-        const int b_mn = 0, grid = 148, lds = 0;
-        mma_rate_kernel<<<grid, 160, 96 * 1024>>>(n, a_mode, b_mn, 64, 0, d, n_acc);  // warm
-        mma_rate_kernel<<<grid, 160, 96 * 1024>>>(n, a_mode, b_mn, iters, lds, d, n_acc);
-        long long c = 0;
-        cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
-        printf("accumulators %d  M=128 N=%3d K=16  %-16s : %7.1f cycles/MMA  (ideal %d)\n", n_acc, n, am[a_mode],
-               double(c) / iters, 128 * n / 256);
-      }
+    for (int a_mode : {0, 1, 2})
+      for (int b_mn : {0, 1})
+        for (int n : {64, 128, 256}) {
+          if (n_acc * n > 448) continue;
+          const int grid = 148, lds = 0;
+          mma_rate_kernel<<<grid, 160, 96 * 1024>>>(n, a_mode, b_mn, 64, 0, d, n_acc);  // warm
+          mma_rate_kernel<<<grid, 160, 96 * 1024>>>(n, a_mode, b_mn, iters, lds, d, n_acc);
+          long long c = 0;
+          cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+          if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+          printf("accumulators %d  M=128 N=%3d K=16  %-16s B %-8s : %7.1f cycles/MMA  (ideal %d)\n", n_acc, n, am[a_mode],
+                 b_mn ? "MN-major" : "K-major", double(c) / iters, 128 * n / 256);
+        }
   return 0;
 }
