@@ -186,6 +186,25 @@ int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8_t* present
                                  int n_pairs, float* logit_scale, int B, int GB, int R, int d, int n_mod, int rank,
                                  const float* w, float* dpooled_all, float* dscale, void* stream);
 
+/* Peer-memory exchange of the pooled block for data parallelism inside one NVLink/NVSwitch domain (replaces the
+ * all_gather / reduce_scatter of utils/distributed.py:23-56 and torch.distributed.nn.functional.all_gather's backward).
+ * The gathered [GB,R,d] buffers live in P2P-mapped symmetric memory, one per rank, addressable by all ranks:
+ *   forward : mca_p2p_push_rows(own block -> slot `rank` of every rank's gathered buffer), mca_xgpu_barrier,
+ *             mca_contrastive_allpairs_fwd on the local gathered buffer;
+ *   backward: mca_contrastive_allpairs_bwd into the local gradient buffer, mca_xgpu_barrier,
+ *             mca_p2p_reduce_rows (sum of every rank's slice of this rank's rows). */
+/* dst_peers_dev[g][off_elems + i] = src[i], i < n, for every rank g (posted NVLink stores). */
+int mca_p2p_push_rows(const float* src, float* const* dst_peers_dev, long long off_elems, long long n, int world,
+                      void* stream);
+/* dst[i] = sum_g src_peers_dev[g][off_elems + i], i < n: the pull form of a reduce-scatter over peer memory. */
+int mca_p2p_reduce_rows(const float* const* src_peers_dev, long long off_elems, float* dst, long long n, int world,
+                        void* stream);
+/* Flag barrier across the GPUs of one node: flags_peers_dev[g] = rank g's uint32[world] flag array (peer-mapped, zeroed
+ * once), epoch_dev = this rank's barrier counter (device, zeroed once).  err_flag_dev is set if a peer does not arrive
+ * within ~10 s (the kernel then returns instead of hanging the GPU). */
+int mca_xgpu_barrier(uint32_t* const* flags_peers_dev, int world, int rank, uint32_t* epoch_dev, int* err_flag_dev,
+                     void* stream);
+
 /* clip_grad_norm_(max_norm) + AdamW + LR schedule on flat buffers (train_accel_gpu.py:80-86,116-119).
  * step_dev: device int64 step counter (incremented here); grads are multiplied by grad_scale first (1/world). */
 int mca_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,

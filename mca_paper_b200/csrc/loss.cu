@@ -6,6 +6,15 @@
 // with zero host synchronisations (the reference does one .item() per pair, model.py:225).
 // `pooled_all` is the all-gathered [G*B, R, d] block; gradients are produced for every gathered row so the host can
 // reduce-scatter them (the autograd of torch.distributed.nn.functional.all_gather, utils/distributed.py:45-46).
+//
+// Peer-memory exchange (data parallel inside one NVLink/NVSwitch domain), replacing the NCCL all_gather /
+// reduce_scatter around these kernels: the gathered blocks live in P2P-mapped symmetric memory; every rank PUSHES its
+// [B, R, d] pooled block into slot `rank` of every peer's gathered buffer (mca_p2p_push_rows: posted NVLink stores, no
+// read latency), a flag barrier (mca_xgpu_barrier) publishes them, the loss kernels then run on local memory; the
+// backward writes its [G*B, R, d] gradient block locally and, after a second barrier, mca_p2p_reduce_rows PULLS and
+// sums every rank's slice of this rank's rows (the reduce-scatter).  (Reading the peers' rows from inside the loss
+// kernels was measured slower: their 2 KB dot-product rows are latency-bound over NVLink.)  Everything is a plain
+// kernel on one stream, so forward + loss + backward stay in one CUDA graph.
 #include <math_constants.h>
 
 #include "mca_b200.h"
@@ -35,6 +44,11 @@ __device__ __forceinline__ float warp_max_f(float v) {
   return v;
 }
 
+// row r of gathered sample j
+__device__ __forceinline__ const float* pooled_row(const LossArgs& a, int j, int r) {
+  return a.pooled_all + (static_cast<long long>(j) * a.R + r) * a.d;
+}
+
 __device__ __forceinline__ bool row_selected(const LossArgs& a, const mca_loss_pair& p, int i) {
   unsigned bits = 0;
   for (int m = 0; m < a.n_mod; ++m) bits |= (a.present[i * a.n_mod + m] ? 1u : 0u) << m;
@@ -51,8 +65,8 @@ __device__ void compute_logits(const LossArgs& a, const mca_loss_pair& p, float 
     const int dir = t / (a.B * a.GB);
     const int i = (t / a.GB) % a.B, j = t % a.GB;
     const int rq = dir == 0 ? p.a_row : p.b_row, rk = dir == 0 ? p.b_row : p.a_row;
-    const float* q = a.pooled_all + (static_cast<long long>(a.rank * a.B + i) * a.R + rq) * a.d;
-    const float* k = a.pooled_all + (static_cast<long long>(j) * a.R + rk) * a.d;
+    const float* q = pooled_row(a, a.rank * a.B + i, rq);
+    const float* k = pooled_row(a, j, rk);
     float acc = 0.f;
     for (int c = lane * 4; c < a.d; c += 128) {
       const float4 x = *reinterpret_cast<const float4*>(q + c);
@@ -184,19 +198,72 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ w, float* __restrict__ dpo
       // d query_i += T sum_j dl[i][j] key_all[j]
       for (int i = 0; i < a.B; ++i) {
         float acc = 0.f;
-        for (int j = 0; j < a.GB; ++j)
-          acc += dl[i * a.GB + j] * a.pooled_all[(static_cast<long long>(j) * a.R + rk) * a.d + c];
+        for (int j = 0; j < a.GB; ++j) acc += dl[i * a.GB + j] * pooled_row(a, j, rk)[c];
         if (acc != 0.f)
           atomicAdd(dpooled_all + (static_cast<long long>(a.rank * a.B + i) * a.R + rq) * a.d + c, T * acc);
       }
       // d key_all[j] += T sum_i dl[i][j] query_i
       for (int j = 0; j < a.GB; ++j) {
         float acc = 0.f;
-        for (int i = 0; i < a.B; ++i)
-          acc += dl[i * a.GB + j] * a.pooled_all[(static_cast<long long>(a.rank * a.B + i) * a.R + rq) * a.d + c];
+        for (int i = 0; i < a.B; ++i) acc += dl[i * a.GB + j] * pooled_row(a, a.rank * a.B + i, rq)[c];
         if (acc != 0.f) atomicAdd(dpooled_all + (static_cast<long long>(j) * a.R + rk) * a.d + c, T * acc);
       }
     }
+  }
+}
+
+// ---- cross-GPU flag barrier over peer-mapped memory.  flags[g] (uint32[G], one array per rank, every rank can address
+// all of them): rank r publishes the barrier's epoch in slot r of EVERY rank's array (release, system scope) and waits
+// until every slot of its own array has reached the epoch (acquire).  The epoch is a device counter, so the same
+// captured graph can be replayed.  A peer that never arrives raises err_flag after ~10 s instead of hanging the GPU.
+__global__ void xgpu_barrier_kernel(uint32_t* const* __restrict__ flags_peers, int world, int rank,
+                                    uint32_t* __restrict__ epoch, int* __restrict__ err_flag) {
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = ++(*epoch);
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  const int g = threadIdx.x;
+  if (g >= world) return;
+  __threadfence_system();  // everything this GPU wrote before the barrier is visible before the flag is
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags_peers[g] + rank), "r"(e) : "memory");
+  const uint32_t* mine = flags_peers[rank] + g;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (static_cast<int32_t>(v - e) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) {
+      atomicExch(err_flag, 1);
+      break;
+    }
+  }
+}
+
+// dst_peers[g][off + i] = src[i] for every rank g (the push form of an all-gather; float4 lanes, posted P2P stores)
+__global__ void __launch_bounds__(256)
+p2p_push_rows_kernel(const float* __restrict__ src, float* const* __restrict__ dst_peers, long long off, long long n4,
+                     int world) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    for (int g = 0; g < world; ++g) reinterpret_cast<float4*>(dst_peers[g] + off)[i] = v;
+  }
+}
+
+// dst[i] = sum over ranks g of src_peers[g][off + i]  (the pull form of a reduce-scatter; float4 lanes, coalesced P2P reads)
+__global__ void __launch_bounds__(256)
+p2p_reduce_rows_kernel(const float* const* __restrict__ src_peers, long long off, float* __restrict__ dst, long long n4,
+                       int world) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < world; ++g) {
+      const float4 v = reinterpret_cast<const float4*>(src_peers[g] + off)[i];
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dst)[i] = acc;
   }
 }
 
@@ -243,5 +310,32 @@ extern "C" int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8
   }
   LossArgs a{pooled_all, present, plan_dev, logit_scale, B, GB, R, d, n_mod, rank, n_pairs};
   loss_bwd_kernel<<<n_pairs, LOSS_THREADS, smem, stream>>>(a, w, dpooled_all, dscale);
+  return check_launch();
+}
+
+extern "C" int mca_xgpu_barrier(uint32_t* const* flags_peers_dev, int world, int rank, uint32_t* epoch_dev,
+                                int* err_flag_dev, void* stream_) {
+  if (world < 1 || world > 32 || rank < 0 || rank >= world) return MCA_ERR_ARG;
+  xgpu_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(flags_peers_dev, world, rank, epoch_dev,
+                                                                             err_flag_dev);
+  return check_launch();
+}
+
+extern "C" int mca_p2p_push_rows(const float* src, float* const* dst_peers_dev, long long off_elems, long long n, int world,
+                                 void* stream_) {
+  if (n <= 0 || (n % 4) != 0 || (off_elems % 4) != 0 || world < 1) return MCA_ERR_SHAPE;
+  const long long n4 = n / 4;
+  const unsigned grid = static_cast<unsigned>((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+  p2p_push_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(src, dst_peers_dev, off_elems, n4, world);
+  return check_launch();
+}
+
+extern "C" int mca_p2p_reduce_rows(const float* const* src_peers_dev, long long off_elems, float* dst, long long n,
+                                   int world, void* stream_) {
+  if (n <= 0 || (n % 4) != 0 || (off_elems % 4) != 0 || world < 1) return MCA_ERR_SHAPE;
+  const long long n4 = n / 4;
+  const unsigned grid = static_cast<unsigned>(n4 + 255) / 256 < 1184u ? static_cast<unsigned>((n4 + 255) / 256) : 1184u;
+  p2p_reduce_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(src_peers_dev, off_elems, dst, n4,
+                                                                                   world);
   return check_launch();
 }

@@ -43,6 +43,7 @@ class Engine:
         self.R = plan.R
         self.device = None
         self.world, self.rank, self.group = 1, 0, None
+        self._p2p = None
         self._ws_ready = False
         self._flat_ptrs = None
         self.check_finite = True
@@ -231,9 +232,58 @@ class Engine:
         self._gather_ws = None
         self._ws_ready = True
 
-    def set_distributed(self, world: int, rank: int, group=None):
+    def set_distributed(self, world: int, rank: int, group=None, p2p: Optional[bool] = None):
+        """Data parallel over `group`.  p2p (default: env MCA_P2P != "0"): keep the gathered pooled block, its gathered
+        gradient and the barrier flags in P2P-mapped symmetric memory and exchange them with our own push / pull
+        kernels over NVLink (no NCCL all_gather / reduce_scatter in the step, the whole forward + loss + backward is
+        one CUDA graph); otherwise the NCCL collectives are used between graph segments."""
+        import os
         self.world, self.rank, self.group = world, rank, group
         self._gather_ws = None
+        self._p2p = None
+        want = (os.environ.get("MCA_P2P", "1") != "0") if p2p is None else p2p
+        if world > 1 and want:
+            self.ensure_flat()
+            self._setup_p2p()
+
+    def _setup_p2p(self):
+        """One symmetric allocation per rank: [pooled_all G*B*R*D | dpooled_all G*B*R*D | flags (G uint32, padded)]."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        dev, G = self.device, self.world
+        n_p = n_d = G * self.B * self.R * D
+        total = n_p + n_d + 64
+        buf = symm.empty(total, dtype=torch.float32, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        # buffer_ptrs are the bases of the symmetric ALLOCATIONS; the tensor may sit at an offset inside its own (the
+        # same offset on every rank, the allocation is symmetric)
+        off = int(buf.data_ptr()) - int(hdl.buffer_ptrs[self.rank])
+        if off < 0 or off + 4 * total > int(hdl.buffer_size):
+            raise _lib.MCAKernelError(f"symmetric-memory tensor outside its allocation (offset {off})")
+        base = [int(p) + off for p in hdl.buffer_ptrs]
+        i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=dev)
+        self._p2p = {
+            "buf": buf, "handle": hdl,
+            "pooled_all": buf[:n_p].view(G * self.B, self.R, D),
+            "dpooled_all": buf[n_p:n_p + n_d].view(G * self.B, self.R, D),
+            "pooled_peers": i64(base),
+            "dall_peers": i64([b + 4 * n_p for b in base]),
+            "flags_peers": i64([b + 4 * (n_p + n_d) for b in base]),
+            "epoch": torch.zeros(1, dtype=torch.int32, device=dev),
+            "err": torch.zeros(1, dtype=torch.int32, device=dev),
+        }
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)  # every rank's flags are zero before anybody raises one
+
+    def xgpu_barrier(self):
+        p = self._p2p
+        call("mca_xgpu_barrier", P(p["flags_peers"]), self.world, self.rank, P(p["epoch"]), P(p["err"]), S())
+
+    def check_p2p(self):
+        """Raises if a peer missed a flag barrier (read once per run, not per step)."""
+        if self._p2p is not None and int(self._p2p["err"].item()) != 0:
+            raise _lib.MCAKernelError("a peer GPU did not reach mca_xgpu_barrier within 10 s")
 
     def _gather_buffers(self):
         if self._gather_ws is None:
@@ -365,18 +415,24 @@ class Engine:
     def loss_forward(self, pooled):
         """All-gather of the pooled block (one collective instead of 2 per pair) + fused all-pairs InfoNCE."""
         ws, g = self.ws, self._gather_buffers()
-        if self.world > 1:
+        s = self.pview("loss.loss_fn.logit_scale")
+        lf = self.model.loss.loss_fn
+        lo = float(lf.logit_scale_min if lf.logit_scale_min is not None else -1e30)
+        hi = float(lf.logit_scale_max if lf.logit_scale_max is not None else 1e30)
+        if self.world > 1 and self._p2p is not None:
+            # peer-memory all-gather: push this rank's block into slot `rank` of every rank's gathered buffer, barrier
+            n = self.B * self.R * D
+            call("mca_p2p_push_rows", P(pooled), P(self._p2p["pooled_peers"]), self.rank * n, n, self.world, S())
+            self.xgpu_barrier()
+            pooled_all = self._p2p["pooled_all"]
+        elif self.world > 1:
             torch.distributed.all_gather_into_tensor(g["pooled_all"], pooled.contiguous(), group=self.group)
             pooled_all = g["pooled_all"]
         else:
             pooled_all = pooled
         self._pooled_all = pooled_all
-        s = self.pview("loss.loss_fn.logit_scale")
-        lf = self.model.loss.loss_fn
         call("mca_contrastive_allpairs_fwd", P(pooled_all), P(ws["present"]), P(self.loss_plan), self.plan.n_pairs, P(s),
-             self.B, self.world * self.B, self.R, D, self.plan.n_mod, self.rank,
-             float(lf.logit_scale_min if lf.logit_scale_min is not None else -1e30),
-             float(lf.logit_scale_max if lf.logit_scale_max is not None else 1e30),
+             self.B, self.world * self.B, self.R, D, self.plan.n_mod, self.rank, lo, hi,
              P(ws["losses"]), P(ws["summary"]), P(ws["w_default"]), S())
         return ws["losses"], ws["summary"]
 
@@ -385,6 +441,20 @@ class Engine:
         """w[p] = dL/d losses[p].  Returns dL/d pooled [B,R,D] (after the reduce-scatter of gathered gradients)."""
         ws, g = self.ws, self._gather_buffers()
         GB = self.world * self.B
+        if self.world > 1 and self._p2p is not None:
+            p = self._p2p
+            # the peers finished pulling last step's gradient slices before they reached this step's first barrier
+            p["dpooled_all"].zero_()
+            g["dscale"].zero_()
+            s = self.pview("loss.loss_fn.logit_scale")
+            call("mca_contrastive_allpairs_bwd", P(self._pooled_all), P(ws["present"]), P(self.loss_plan),
+                 self.plan.n_pairs, P(s), self.B, GB, self.R, D, self.plan.n_mod, self.rank, P(w), P(p["dpooled_all"]),
+                 P(g["dscale"]), S())
+            self.xgpu_barrier()
+            n = self.B * self.R * D
+            call("mca_p2p_reduce_rows", P(p["dall_peers"]), self.rank * n, P(g["dpooled"]), n, self.world, S())
+            self.gview("loss.loss_fn.logit_scale").add_(g["dscale"].view(()))
+            return g["dpooled"]
         dall = g["dpooled_all"] if self.world > 1 else g["dpooled"]
         dall.zero_()
         g["dscale"].zero_()

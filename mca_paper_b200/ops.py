@@ -48,6 +48,9 @@ _SIGS = {
     "mca_small_gemm_f32": [VP, I64, I64, VP, I64, I64, VP, I64, VP, I64, I32, I32, I32, I32, F32, I32, VP],
     "mca_contrastive_allpairs_fwd": [VP, VP, VP, I32, VP, I32, I32, I32, I32, I32, I32, F32, F32, VP, VP, VP, VP],
     "mca_contrastive_allpairs_bwd": [VP, VP, VP, I32, VP, I32, I32, I32, I32, I32, I32, VP, VP, VP, VP],
+    "mca_p2p_push_rows": [VP, VP, I64, I64, I32, VP],
+    "mca_xgpu_barrier": [VP, I32, I32, VP, VP, VP],
+    "mca_p2p_reduce_rows": [VP, I64, VP, I64, I32, VP],
     "mca_clip_adamw_step": [VP, VP, VP, VP, I64, VP, VP, VP, F32, VP, VP],
     "mca_tabular_fwd": [VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_tabular_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],

@@ -5,9 +5,11 @@ Replaces the reference hot loop train_accel_gpu.py:110-119 (move_to, model(batch
 clip_grad_norm_, optimizer.step, lr_scheduler.step) without its per-step host synchronisations
 (train_accel_gpu.py:126-130 log every scalar with .to("cpu"); here the loss stays on the device until asked for).
 
-Data parallelism: one process per GPU, identical replicas, B samples per rank; three collectives per
-step over NCCL/NVLink — all-gather of the pooled block [B,R,512], reduce-scatter of its gradient, all-reduce of the
-flat gradient buffer — issued between graph segments.
+Data parallelism: one process per GPU, identical replicas, B samples per rank.  The exchange of the pooled
+block [B,R,512] and the reduce-scatter of its gradient run inside the loss kernels over P2P-mapped symmetric memory
+(NVLink loads behind a flag barrier), so forward + loss + backward are ONE captured graph; only the all-reduce of the
+flat gradient buffer is an NCCL call between that graph and the optimiser.  MCA_P2P=0 selects the NCCL
+all_gather / reduce_scatter form (three collectives between graph segments).
 """
 from __future__ import annotations
 
@@ -136,15 +138,21 @@ class Trainer:
             with torch.cuda.graph(g):
                 self._run_eager()
             self._graphs = [("graph", g)]
+        elif eng._p2p is not None:
+            # peer-memory loss exchange: forward + loss + backward in one graph, then NCCL all-reduce + optimiser
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._seg_forward()
+                self._seg_loss()
+                self._seg_backward()
+            self._graphs = [("graph", g1), ("eager", self._seg_optim)]
         else:
             # collectives stay outside the graphs: [fwd] all_gather+loss(eager: contains 2 collectives) [bwd] all_reduce+optim
             g1, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 self._seg_forward()
-            self._seg_loss()
-            with torch.cuda.graph(g3, pool=g1.pool()):
+            with torch.cuda.graph(g3, pool=g1.pool()):   # consumes the buffers the (eager) loss segment fills
                 self._seg_backward()
-            self._seg_optim()
             self._graphs = [("graph", g1), ("eager", self._seg_loss), ("graph", g3), ("eager", self._seg_optim)]
         torch.cuda.synchronize()
 

@@ -30,12 +30,25 @@ chk = torch.stack([eng.flat.double().sum(), eng.flat.double().abs().sum(), eng.e
 allc = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(allc, chk)
 same = all(torch.equal(allc[0], c) for c in allc)
-# rank-local loss vs oracle on the gathered pooled block of the LAST forward
-pooled_all = eng._pooled_all.float().cpu()
-present = eng.ws["present"].cpu()
+eng.check_p2p()
+# same weights, same batch: the peer-memory loss exchange against the NCCL all_gather / reduce_scatter form
+if eng._p2p is not None:
+    pooled = eng.trunk_forward(tr._dev_batch)
+    l_a = eng.loss_forward(pooled)[0].clone()
+    d_a = eng.loss_backward(eng.ws["w_default"]).clone()
+    saved, eng._p2p = eng._p2p, None
+    l_b = eng.loss_forward(pooled)[0].clone()
+    d_b = eng.loss_backward(eng.ws["w_default"]).clone()
+    eng._p2p = saved
+    torch.cuda.synchronize()
+    dl = (l_a - l_b).abs().nan_to_num().max().item()
+    dd = ((d_a - d_b).norm() / d_b.norm()).item()
+    print(f"rank {rank}: p2p vs nccl  max |dloss| {dl:.3e}  rel |d dpooled| {dd:.3e}  losses[:4] {l_a[:4].tolist()} / {l_b[:4].tolist()}", flush=True)
+    assert dl < 1e-4 and dd < 1e-5, "peer-memory loss path disagrees with the NCCL path"
+mode = "p2p (symmetric memory)" if eng._p2p is not None else "nccl all_gather/reduce_scatter"
 if rank == 0:
-    from oracle import mca_oracle as O
-    print(f"world {world}: losses rank0 {losses}; replicas identical: {same}; pooled_all {tuple(pooled_all.shape)}", flush=True)
+    print(f"world {world} [{mode}]: losses rank0 {[f'{l:.6f}' for l in losses]}; replicas identical: {same}; "
+          f"param checksum {allc[0][1].item():.6f}", flush=True)
     assert same, "replicas diverged"
     assert all(l == l for l in losses), "NaN loss"
 dist.barrier()
