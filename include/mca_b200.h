@@ -201,15 +201,29 @@ int mca_p2p_reduce_rows(const float* const* src_peers_dev, long long off_elems, 
                         void* stream);
 /* Flag barrier across the GPUs of one node: flags_peers_dev[g] = rank g's uint32[world] flag array (peer-mapped, zeroed
  * once), epoch_dev = this rank's barrier counter (device, zeroed once).  err_flag_dev is set if a peer does not arrive
- * within ~10 s (the kernel then returns instead of hanging the GPU). */
+ * within ~10 s (the kernel then returns instead of hanging the GPU).  Optional payload: *payload (one double of this
+ * rank) is stored into payload_peers_dev[g][rank] of every rank before the flag is raised. */
 int mca_xgpu_barrier(uint32_t* const* flags_peers_dev, int world, int rank, uint32_t* epoch_dev, int* err_flag_dev,
-                     void* stream);
+                     const double* payload, double* const* payload_peers_dev, void* stream);
 
 /* clip_grad_norm_(max_norm) + AdamW + LR schedule on flat buffers (train_accel_gpu.py:80-86,116-119).
  * step_dev: device int64 step counter (incremented here); grads are multiplied by grad_scale first (1/world). */
 int mca_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                         double* sumsq_scratch, long long* step_dev, float* total_norm_out, float grad_scale,
                         const mca_adamw_cfg* cfg_host, void* stream);
+
+/* Data-parallel optimiser over peer memory (replaces DDP's gradient all-reduce, train_accel_gpu.py:93,115, followed by
+ * clip_grad_norm_ + AdamW on every rank): rank r owns flat elements [shard_off, shard_off + shard_n).
+ * mca_dp_reduce_shard: grads_local[shard] = sum_g grads_peers_dev[g][shard] (pulled over NVLink), *sumsq_local = its sum
+ * of squares.  After a barrier that carries the G partial sums (mca_xgpu_barrier payload), mca_dp_adamw_shard clips by the
+ * global norm, applies AdamW to the shard (moments of the shard only) and stores the new parameters into
+ * params_peers_dev[g][shard] of EVERY rank (all-gather by posted stores); a last barrier publishes them. */
+int mca_dp_reduce_shard(const float* const* grads_peers_dev, float* grads_local, long long shard_off, long long shard_n,
+                        int world, double* sumsq_local, void* stream);
+int mca_dp_adamw_shard(float* const* params_peers_dev, int world, int rank, const float* grads_local, float* exp_avg,
+                       float* exp_avg_sq, long long shard_off, long long shard_n, const double* sumsq_slots,
+                       long long* step_dev, float* total_norm_out, float grad_scale, const mca_adamw_cfg* cfg_host,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -216,14 +216,18 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ w, float* __restrict__ dpo
 // all of them): rank r publishes the barrier's epoch in slot r of EVERY rank's array (release, system scope) and waits
 // until every slot of its own array has reached the epoch (acquire).  The epoch is a device counter, so the same
 // captured graph can be replayed.  A peer that never arrives raises err_flag after ~10 s instead of hanging the GPU.
+// Optional payload: one double of this rank (e.g. its partial gradient sum of squares) is stored into slot `rank` of
+// every rank's payload array before the flag is raised, so it is visible to whoever passes the barrier.
 __global__ void xgpu_barrier_kernel(uint32_t* const* __restrict__ flags_peers, int world, int rank,
-                                    uint32_t* __restrict__ epoch, int* __restrict__ err_flag) {
+                                    uint32_t* __restrict__ epoch, int* __restrict__ err_flag,
+                                    const double* __restrict__ payload, double* const* __restrict__ payload_peers) {
   __shared__ uint32_t s_epoch;
   if (threadIdx.x == 0) s_epoch = ++(*epoch);
   __syncthreads();
   const uint32_t e = s_epoch;
   const int g = threadIdx.x;
   if (g >= world) return;
+  if (payload != nullptr) payload_peers[g][rank] = *payload;
   __threadfence_system();  // everything this GPU wrote before the barrier is visible before the flag is
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags_peers[g] + rank), "r"(e) : "memory");
   const uint32_t* mine = flags_peers[rank] + g;
@@ -314,10 +318,12 @@ extern "C" int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8
 }
 
 extern "C" int mca_xgpu_barrier(uint32_t* const* flags_peers_dev, int world, int rank, uint32_t* epoch_dev,
-                                int* err_flag_dev, void* stream_) {
+                                int* err_flag_dev, const double* payload, double* const* payload_peers_dev,
+                                void* stream_) {
   if (world < 1 || world > 32 || rank < 0 || rank >= world) return MCA_ERR_ARG;
+  if (payload != nullptr && payload_peers_dev == nullptr) return MCA_ERR_ARG;
   xgpu_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(flags_peers_dev, world, rank, epoch_dev,
-                                                                             err_flag_dev);
+                                                                             err_flag_dev, payload, payload_peers_dev);
   return check_launch();
 }
 

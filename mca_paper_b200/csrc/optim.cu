@@ -76,6 +76,94 @@ clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
   }
 }
 
+// ---- data-parallel optimiser over peer memory (one NVLink/NVSwitch domain), ZeRO-1 style: rank r owns the elements
+// [off, off + n) of the flat buffers.  Instead of an NCCL all-reduce followed by a full AdamW on every rank:
+//   dp_reduce_shard : own shard of the gradient = sum over ranks, PULLED from the peers' gradient buffers (coalesced
+//                     float4 NVLink reads), written back into the local gradient buffer; partial sum of squares
+//   (barrier carrying the partial sums of squares to every rank)
+//   dp_adamw_shard  : global norm from the G partials, clip + AdamW on the own shard only (1/G of the optimiser
+//                     traffic), the new parameters PUSHED into every rank's parameter buffer (the all-gather, as posted
+//                     NVLink stores from inside the update kernel)
+// Every rank ends the step with bit-identical parameters.
+__global__ void __launch_bounds__(256)
+dp_reduce_shard_kernel(const float* const* __restrict__ grads_peers, float* __restrict__ grads_local, long long off,
+                       long long n, int world, double* __restrict__ sumsq_local) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const long long n4 = n / 4;  // shards are multiples of 4 elements
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < world; ++g) {
+      const float4 q = reinterpret_cast<const float4*>(grads_peers[g] + off)[i];
+      t.x += q.x, t.y += q.y, t.z += q.z, t.w += q.w;
+    }
+    reinterpret_cast<float4*>(grads_local + off)[i] = t;
+    acc += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(sumsq_local, static_cast<double>(t));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dp_adamw_shard_kernel(float* const* __restrict__ params_peers, int world, int rank, const float* __restrict__ g,
+                      float* __restrict__ m, float* __restrict__ v, long long off, long long n,
+                      const double* __restrict__ sumsq_slots, const long long* __restrict__ step_ptr, float grad_scale,
+                      mca_adamw_cfg c, float* __restrict__ total_norm_out) {
+  __shared__ float s_coef, s_lr, s_bc1, s_bc2s;
+  if (threadIdx.x == 0) {
+    const long long step = *step_ptr + 1;
+    double ss = 0.0;
+    for (int r = 0; r < world; ++r) ss += sumsq_slots[r];  // same order on every rank
+    const float total = static_cast<float>(sqrt(ss)) * grad_scale;
+    if (blockIdx.x == 0 && total_norm_out != nullptr) *total_norm_out = total;
+    float coef = 1.0f;
+    if (c.max_norm > 0.f) coef = fminf(1.0f, c.max_norm / (total + 1e-6f));
+    s_coef = coef * grad_scale;
+    s_lr = scheduled_lr(c, step);
+    s_bc1 = static_cast<float>(1.0 - pow(static_cast<double>(c.beta1), static_cast<double>(step)));
+    s_bc2s = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(c.beta2), static_cast<double>(step))));
+  }
+  __syncthreads();
+  const float coef = s_coef, lr = s_lr, bc1 = s_bc1, bc2s = s_bc2s;
+  const float decay = 1.0f - lr * c.weight_decay;
+  const float step_size = lr / bc1;
+  const float* p_own = params_peers[rank] + off;
+  const long long n4 = n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 gq = reinterpret_cast<const float4*>(g + off)[i];
+    float4 mq = reinterpret_cast<const float4*>(m + off)[i];
+    float4 vq = reinterpret_cast<const float4*>(v + off)[i];
+    float4 pq = reinterpret_cast<const float4*>(p_own)[i];
+    const float gs[4] = {gq.x * coef, gq.y * coef, gq.z * coef, gq.w * coef};
+    float* mm = reinterpret_cast<float*>(&mq);
+    float* vv = reinterpret_cast<float*>(&vq);
+    float* pp = reinterpret_cast<float*>(&pq);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] = c.beta1 * mm[k] + (1.0f - c.beta1) * gs[k];
+      vv[k] = c.beta2 * vv[k] + (1.0f - c.beta2) * gs[k] * gs[k];
+      const float denom = sqrtf(vv[k]) / bc2s + c.eps;
+      pp[k] = pp[k] * decay - step_size * (mm[k] / denom);
+    }
+    reinterpret_cast<float4*>(m + off)[i] = mq;
+    reinterpret_cast<float4*>(v + off)[i] = vq;
+    for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(params_peers[r] + off)[i] = pq;
+  }
+}
+
+__global__ void bump_step_only_kernel(long long* step_ptr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *step_ptr += 1;
+}
+
 __global__ void bump_step_kernel(long long* step_ptr, double* sumsq, float* total_norm_out, float grad_scale) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     *step_ptr += 1;
@@ -98,5 +186,31 @@ extern "C" int mca_clip_adamw_step(float* params, const float* grads, float* exp
   clip_adamw_kernel<<<blocks, 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, sumsq_scratch, step_dev,
                                                grad_scale, *cfg_host);
   bump_step_kernel<<<1, 32, 0, stream>>>(step_dev, sumsq_scratch, total_norm_out, grad_scale);
+  return check_launch();
+}
+
+extern "C" int mca_dp_reduce_shard(const float* const* grads_peers_dev, float* grads_local, long long shard_off,
+                                   long long shard_n, int world, double* sumsq_local, void* stream_) {
+  if (shard_n < 0 || (shard_n % 4) != 0 || (shard_off % 4) != 0 || world < 1) return MCA_ERR_SHAPE;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (cudaMemsetAsync(sumsq_local, 0, sizeof(double), stream) != cudaSuccess) return MCA_ERR_CUDA;
+  if (shard_n == 0) return MCA_OK;
+  dp_reduce_shard_kernel<<<num_sms() * 4, 256, 0, stream>>>(grads_peers_dev, grads_local, shard_off, shard_n, world,
+                                                            sumsq_local);
+  return check_launch();
+}
+
+extern "C" int mca_dp_adamw_shard(float* const* params_peers_dev, int world, int rank, const float* grads_local,
+                                  float* exp_avg, float* exp_avg_sq, long long shard_off, long long shard_n,
+                                  const double* sumsq_slots, long long* step_dev, float* total_norm_out,
+                                  float grad_scale, const mca_adamw_cfg* cfg_host, void* stream_) {
+  if (shard_n < 0 || (shard_n % 4) != 0 || (shard_off % 4) != 0 || world < 1 || rank < 0 || rank >= world)
+    return MCA_ERR_SHAPE;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (shard_n > 0)
+    dp_adamw_shard_kernel<<<num_sms() * 4, 256, 0, stream>>>(params_peers_dev, world, rank, grads_local, exp_avg,
+                                                             exp_avg_sq, shard_off, shard_n, sumsq_slots, step_dev,
+                                                             grad_scale, *cfg_host, total_norm_out);
+  bump_step_only_kernel<<<1, 32, 0, stream>>>(step_dev);
   return check_launch();
 }

@@ -66,13 +66,14 @@ class Engine:
         for name, p in params:
             offs[name] = total
             total += _round_up(p.numel(), ALIGN)
-        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.device = dev
+        flat, self._flat_peers = self._alloc_flat(total)
         for name, p in params:
             o = offs[name]
             flat[o:o + p.numel()].copy_(p.detach().reshape(-1).to(torch.float32))
             p.data = flat[o:o + p.numel()].view(p.shape)
         self.flat, self.offs, self.n_flat = flat, offs, total
-        self.flat_grad = torch.zeros_like(flat)
+        self.flat_grad, self._grad_peers = self._alloc_flat(total)
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
@@ -83,6 +84,24 @@ class Engine:
         self._build_static(dev)
         self._build_pack_descs(dev)
         self._alloc_workspace(dev)
+
+    def _alloc_flat(self, total):
+        """fp32 [total] zeros.  Under peer-memory data parallelism the buffer comes from P2P-mapped symmetric memory
+        (collective call: every rank allocates in the same order) and the peers' addresses are returned with it."""
+        dev = self.device
+        if not getattr(self, "_want_symm", False):
+            return torch.zeros(total, device=dev, dtype=torch.float32), None
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        buf = symm.empty(total, dtype=torch.float32, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        off = int(buf.data_ptr()) - int(hdl.buffer_ptrs[self.rank])
+        if off < 0 or off + 4 * total > int(hdl.buffer_size):
+            raise _lib.MCAKernelError(f"symmetric-memory tensor outside its allocation (offset {off})")
+        self._symm_keep = getattr(self, "_symm_keep", []) + [(buf, hdl)]
+        peers = torch.tensor([int(p) + off for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        return buf, peers
 
     def pview(self, name):  # fp32 view of a parameter inside the flat buffer
         p = dict(self._param_list())[name]
@@ -243,16 +262,21 @@ class Engine:
         self._p2p = None
         want = (os.environ.get("MCA_P2P", "1") != "0") if p2p is None else p2p
         if world > 1 and want:
+            # rebuild the flat parameter / gradient buffers in symmetric memory (peers pull gradient shards from them and
+            # push updated parameter shards into them), then the small exchange buffers
+            self._want_symm = True
+            self._flat_ptrs = None
             self.ensure_flat()
             self._setup_p2p()
 
     def _setup_p2p(self):
-        """One symmetric allocation per rank: [pooled_all G*B*R*D | dpooled_all G*B*R*D | flags (G uint32, padded)]."""
+        """One symmetric allocation per rank: [pooled_all G*B*R*D | dpooled_all G*B*R*D | flags (G uint32, padded to 64
+        words) | gradient sum-of-squares slots (G doubles, padded to 32)]."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         dev, G = self.device, self.world
         n_p = n_d = G * self.B * self.R * D
-        total = n_p + n_d + 64
+        total = n_p + n_d + 64 + 64
         buf = symm.empty(total, dtype=torch.float32, device=dev)
         buf.zero_()
         hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
@@ -270,15 +294,27 @@ class Engine:
             "pooled_peers": i64(base),
             "dall_peers": i64([b + 4 * n_p for b in base]),
             "flags_peers": i64([b + 4 * (n_p + n_d) for b in base]),
+            "slots": buf[n_p + n_d + 64:n_p + n_d + 128].view(torch.float64),
+            "slots_peers": i64([b + 4 * (n_p + n_d + 64) for b in base]),
+            "sumsq_local": torch.zeros(1, dtype=torch.float64, device=dev),
+            "grad_peers": self._grad_peers, "param_peers": self._flat_peers,
             "epoch": torch.zeros(1, dtype=torch.int32, device=dev),
             "err": torch.zeros(1, dtype=torch.int32, device=dev),
         }
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)  # every rank's flags are zero before anybody raises one
 
-    def xgpu_barrier(self):
+    def xgpu_barrier(self, payload=None):
+        """Flag barrier over peer memory; `payload` (a device double) is delivered to slot `rank` of every rank's slots."""
         p = self._p2p
-        call("mca_xgpu_barrier", P(p["flags_peers"]), self.world, self.rank, P(p["epoch"]), P(p["err"]), S())
+        call("mca_xgpu_barrier", P(p["flags_peers"]), self.world, self.rank, P(p["epoch"]), P(p["err"]), P(payload),
+             P(p["slots_peers"]) if payload is not None else None, S())
+
+    def shard(self):
+        """Flat-buffer range [off, off + n) this rank owns in the sharded optimiser step."""
+        per = ((self.n_flat + self.world - 1) // self.world + 3) // 4 * 4
+        off = min(self.rank * per, self.n_flat)
+        return off, max(0, min(per, self.n_flat - off))
 
     def check_p2p(self):
         """Raises if a peer missed a flag barrier (read once per run, not per step)."""
@@ -570,7 +606,21 @@ class Engine:
                                       1 if schedule == "cosine" else 0, warmup_steps, total_steps)
 
     def optimizer_step(self):
-        """Gradient all-reduce (data parallel mean, train_accel_gpu.py:93,115) + clip + AdamW + weight re-pack."""
+        """Gradient all-reduce (data parallel mean, train_accel_gpu.py:93,115) + clip + AdamW + weight re-pack.
+        Peer-memory form: reduce-scatter by pulling gradient shards, AdamW on the own shard, all-gather by pushing the
+        updated parameters — three flag barriers, no NCCL call, capturable in the step's CUDA graph."""
+        if self.world > 1 and self._p2p is not None:
+            p = self._p2p
+            off, n = self.shard()
+            self.xgpu_barrier()                                  # every rank's gradient buffer is complete
+            call("mca_dp_reduce_shard", P(p["grad_peers"]), P(self.flat_grad), off, n, self.world, P(p["sumsq_local"]), S())
+            self.xgpu_barrier(payload=p["sumsq_local"])          # + the G partial sums of squares, everywhere
+            call("mca_dp_adamw_shard", P(p["param_peers"]), self.world, self.rank, P(self.flat_grad), P(self.exp_avg),
+                 P(self.exp_avg_sq), off, n, P(p["slots"]), P(self.step_dev), P(self.total_norm), 1.0 / self.world,
+                 ctypes.addressof(self.adamw_cfg), S())
+            self.xgpu_barrier()                                  # every parameter shard has landed
+            self.pack_weights()
+            return
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.group)
         call("mca_clip_adamw_step", P(self.flat), P(self.flat_grad), P(self.exp_avg), P(self.exp_avg_sq), self.n_flat,

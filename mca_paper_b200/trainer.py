@@ -6,10 +6,10 @@ clip_grad_norm_, optimizer.step, lr_scheduler.step) without its per-step host sy
 (train_accel_gpu.py:126-130 log every scalar with .to("cpu"); here the loss stays on the device until asked for).
 
 Data parallelism: one process per GPU, identical replicas, B samples per rank.  The exchange of the pooled
-block [B,R,512] and the reduce-scatter of its gradient run inside the loss kernels over P2P-mapped symmetric memory
-(NVLink loads behind a flag barrier), so forward + loss + backward are ONE captured graph; only the all-reduce of the
-flat gradient buffer is an NCCL call between that graph and the optimiser.  MCA_P2P=0 selects the NCCL
-all_gather / reduce_scatter form (three collectives between graph segments).
+block [B,R,512], the reduce-scatter of its gradient and the gradient reduction + parameter exchange of the optimiser all
+run as our own push / pull kernels over P2P-mapped symmetric memory behind flag barriers (loss.cu, optim.cu), so the whole
+step is ONE captured graph at any world size.  MCA_P2P=0 selects the NCCL form (all_gather, reduce_scatter, all_reduce
+between graph segments).
 """
 from __future__ import annotations
 
@@ -133,19 +133,12 @@ class Trainer:
                 self._run_eager()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        if eng.world == 1:
+        if eng.world == 1 or eng._p2p is not None:
+            # single GPU, or data parallel over peer memory (every exchange is one of our kernels): ONE graph
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._run_eager()
             self._graphs = [("graph", g)]
-        elif eng._p2p is not None:
-            # peer-memory loss exchange: forward + loss + backward in one graph, then NCCL all-reduce + optimiser
-            g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                self._seg_forward()
-                self._seg_loss()
-                self._seg_backward()
-            self._graphs = [("graph", g1), ("eager", self._seg_optim)]
         else:
             # collectives stay outside the graphs: [fwd] all_gather+loss(eager: contains 2 collectives) [bwd] all_reduce+optim
             g1, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()

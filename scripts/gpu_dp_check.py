@@ -26,7 +26,9 @@ for step in range(3):
     losses.append(float(s[0]))
 torch.cuda.synchronize()
 # replicas identical?
-chk = torch.stack([eng.flat.double().sum(), eng.flat.double().abs().sum(), eng.exp_avg.double().abs().sum()])
+# (the peer-memory optimiser keeps AdamW moments only for the rank's own shard: compare parameters there)
+chk = torch.stack([eng.flat.double().sum(), eng.flat.double().abs().sum(),
+                   eng.exp_avg.double().abs().sum() if eng._p2p is None else eng.flat.double().pow(2).sum()])
 allc = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(allc, chk)
 same = all(torch.equal(allc[0], c) for c in allc)

@@ -148,3 +148,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_optimizer_shards_partition_the_flat_buffer():
+    """Peer-memory data parallelism: rank r owns flat elements [off, off + n); the shards must tile [0, n_flat)
+    exactly, in float4 units, for every world size."""
+    from types import SimpleNamespace
+    from mca_paper_b200.engine import Engine
+    for n_flat in (64, 4096, 17_413_888, 19_149_376):
+        for world in (1, 2, 3, 4, 8):
+            pos = 0
+            for rank in range(world):
+                off, n = Engine.shard(SimpleNamespace(n_flat=n_flat, world=world, rank=rank))
+                assert off % 4 == 0 and n % 4 == 0 and n >= 0
+                assert off == min(pos, n_flat)
+                pos = off + n
+            assert pos == n_flat
