@@ -138,6 +138,26 @@ int mca_tabular_bwd(const float* dh1, const float* values, const float* w1, cons
 int mca_pack_weights(const float* params, void* arena_bf16, const mca_pack_desc* descs_dev, int n_desc, void* stream);
 int mca_unpack_grads(float* grads, const float* partials, const mca_pack_desc* descs_dev, int n_desc, void* stream);
 
+/* Index-driven embedding tables: SequenceEncoder (encoders.py:145-166) and SparseTabularEncoder (:100-120) look rows up
+ * by int64 indices [B, L].  nn.Embedding(max_norm) renormalises the LOOKED-UP rows in place, once each
+ * (flags_scratch: uint8[rows], zero on entry and exit); an out-of-range index sets bit 1 of *bad_index_flag.
+ * gather: dst[b*dst_rows_per_b + dst_row_off + l] (+)= emb[idx[b,l]] (+ pe[l]); scatter_add: the gradient of the
+ * gather into demb, skipping row skip_row (padding_idx gets no gradient). */
+int mca_embedding_renorm_indexed(float* emb, const long long* idx, long long n_idx, int rows, int d, float max_norm,
+                                 uint8_t* flags_scratch, int* bad_index_flag, void* stream);
+int mca_embedding_gather(const float* emb, const long long* idx, int rows_emb, int B, int L, int d, const float* pe,
+                         float* dst, int dst_rows_per_b, int dst_row_off, int accumulate, void* stream);
+int mca_embedding_scatter_add(const float* dsrc, const long long* idx, int rows_emb, int B, int L, int d,
+                              int src_rows_per_b, int src_row_off, int skip_row, float* demb, void* stream);
+/* PatchEncoder "matrix" mode (encoders.py:217-274): values [B,H,W] -> tokens [B*(H/p1)*(W/p2), p1*p2] in
+ * 'b (h p1) (w p2) -> b (h w) (p1 p2)' order, mask[t] = all(patch == pad_token). */
+int mca_patchify(const float* values, int B, int H, int W, int p1, int p2, float pad_token, float* tokens, uint8_t* mask,
+                 void* stream);
+/* nn.Dropout(p) on the token rows [b*rows_per_b + row_off + l, :d]: counter-based mask from (seed, *counter_dev,
+ * element), so calling it again with the same counter on the gradient applies the same mask (no stored mask). */
+int mca_dropout_rows(float* x, int B, int L, int d, int rows_per_b, int row_off, float p, unsigned long long seed,
+                     const long long* counter_dev, void* stream);
+
 /* fusion tokens: broadcast into the packed buffer (model.py:460-461) / batch-sum of their gradient */
 int mca_broadcast_rows(const float* src, float* dst, int F, int d, int B, int rows_per_b, int row_off, void* stream);
 int mca_batchsum_rows(const float* src, float* out, int F, int d, int B, int rows_per_b, int row_off, int accumulate,

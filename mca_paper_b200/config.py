@@ -157,6 +157,16 @@ def tiny_config(kind: str = "cmu", zorro: bool = False, fcl: bool = True, bimoda
             "OpenFace": {"type": "EmbeddedSequenceEncoder", "input_size": 713, "max_tokens": 70},
             "glove_vectors": {"type": "EmbeddedSequenceEncoder", "input_size": 300, "max_tokens": 20},
         }
+    elif kind == "mixed":
+        # the three encoder types no shipped config uses next to one EmbeddedSequenceEncoder
+        enc = {
+            "text": {"type": "SequenceEncoder", "num_embeddings": 60, "max_tokens": 40, "padding_idx": 0},
+            "cells": {"type": "SparseTabularEncoder", "num_embeddings": 48, "max_tokens": 28, "padding_idx": 0,
+                      "max_value": 100},
+            "spectrogram": {"type": "PatchEncoder", "patch_size": [4, 8], "mode": "matrix", "max_tokens": 24,
+                            "dropout": 0.0, "height": 16, "width": 48},
+            "COVAREP": {"type": "EmbeddedSequenceEncoder", "input_size": 74, "max_tokens": 50},
+        }
     else:
         enc = {
             "gene": {"type": "TabularEncoder", "num_embeddings": 90, "max_tokens": 90, "max_value": 100},

@@ -23,7 +23,7 @@
 
 namespace mca {
 
-constexpr int LOSS_THREADS = 256;
+constexpr int LOSS_THREADS = 512;  // one thread per embedding column in the backward, 16 warps of dot products
 
 struct LossArgs {
   const float* pooled_all;  // [GB, R, d]

@@ -1,12 +1,9 @@
 """Modality encoders with the reference's constructor surface and state_dict names (encoders.py:17-283).
 
-The modules only *hold* parameters/buffers (so checkpoints of the reference load unchanged); all arithmetic of the
-two encoder types the shipped configs use — EmbeddedSequenceEncoder (CMU) and TabularEncoder (TCGA) — runs in the
-fused CUDA path driven by mca_paper_b200.engine.Engine.encode(), which writes tokens straight into the packed
-[B, N, 512] buffer.  Calling an encoder on its own (`encoder(batch) -> (tokens, attention_mask)`, the reference's
-module-level contract) goes through the same kernels via a single-modality engine.  SequenceEncoder,
-SparseTabularEncoder and PatchEncoder (not exercised by any shipped config) keep the constructor /
-state_dict surface; their kernels are listed as next in DESIGN.md and calling them raises.
+The modules only *hold* parameters/buffers (so checkpoints of the reference load unchanged); the arithmetic of all five
+encoder types — EmbeddedSequenceEncoder (CMU), TabularEncoder (TCGA), and SequenceEncoder / SparseTabularEncoder /
+PatchEncoder (no shipped config uses them) — runs in the fused CUDA path driven by
+mca_paper_b200.engine.Engine.encode(), which writes tokens straight into the packed [B, N, 512] buffer.
 """
 from __future__ import annotations
 
@@ -60,9 +57,10 @@ class _EncoderBase(nn.Module):
         raise NotImplementedError
 
     def forward(self, batch):
-        from .standalone import run_single_encoder
-
-        return run_single_encoder(self, batch)
+        raise NotImplementedError(
+            f"{type(self).__name__} holds parameters only: its arithmetic runs inside the fused MCA path "
+            "(mca_paper_b200.engine.Engine.encode, called by MCA.forward), which writes the tokens straight into the "
+            "packed [B, N, 512] buffer")
 
 
 class EmbeddedSequenceEncoder(_EncoderBase):
@@ -96,50 +94,65 @@ class TabularEncoder(_EncoderBase):
                 "max_value": self.max_value, "padding_idx": self.padding_idx}
 
 
-class SparseTabularEncoder(nn.Module):
-    """encoders.py:100-120 — surface only."""
+class SparseTabularEncoder(_EncoderBase):
+    """encoders.py:100-120: batch {'indices': int64 [B,L], 'data': f32 [B,L], 'attention_mask'}; tokens =
+    Embedding(indices) + ContinuousValueEncoder(data) (its pad test is `data == padding_idx`)."""
+    kind = "SparseTabularEncoder"
 
-    def __init__(self, num_embeddings=36602, embedding_dim=512, padding_idx=0, dropout=0.0, max_value=10000, **kwargs):
+    def __init__(self, num_embeddings=36602, embedding_dim=512, padding_idx=0, dropout=0.0, max_value=10000,
+                 max_tokens=1024, **kwargs):
         super().__init__()
+        self.num_embeddings, self.padding_idx, self.max_value, self.max_tokens = num_embeddings, padding_idx, max_value, max_tokens
         self.token_encoder = TokenEncoder(num_embeddings, embedding_dim, padding_idx)
         self.value_encoder = ContinuousValueEncoder(embedding_dim, dropout, max_value, padding_idx)
 
-    def forward(self, batch):
-        raise NotImplementedError("SparseTabularEncoder has no sm_100a kernel yet (not used by any shipped config)")
+    def _spec(self):
+        return {"type": self.kind, "num_embeddings": self.num_embeddings, "max_tokens": self.max_tokens,
+                "max_value": self.max_value, "padding_idx": self.padding_idx}
 
 
-class SequenceEncoder(nn.Module):
-    """encoders.py:145-166 — surface only."""
+class SequenceEncoder(_EncoderBase):
+    """encoders.py:145-166: batch {'tokens': int64 [B,L], 'attention_mask'}; tokens = Embedding(tokens) + sinusoidal PE."""
+    kind = "SequenceEncoder"
 
     def __init__(self, num_embeddings=36602, embedding_dim=512, padding_idx=0, dropout=0.0, max_tokens=1024, **kwargs):
         super().__init__()
+        self.num_embeddings, self.padding_idx, self.max_tokens = num_embeddings, padding_idx, max_tokens
         self.token_encoder = TokenEncoder(num_embeddings, embedding_dim, padding_idx)
         self.positional_encoder = PositionalEncoder(embedding_dim, dropout, max_tokens)
 
-    def forward(self, batch):
-        raise NotImplementedError("SequenceEncoder has no sm_100a kernel yet (not used by any shipped config)")
+    def _spec(self):
+        return {"type": self.kind, "num_embeddings": self.num_embeddings, "max_tokens": self.max_tokens,
+                "padding_idx": self.padding_idx}
 
 
-class PatchEncoder(nn.Module):
-    """encoders.py:217-274 ("matrix" mode) — surface only."""
+class PatchEncoder(_EncoderBase):
+    """encoders.py:217-274, "matrix" mode (the only mode whose forward works in the reference: `image` / `video`
+    never set `self.layer`, which its attention-mask line needs): values [B,H,W] -> patches 'b (h p1) (w p2) ->
+    b (h w) (p1 p2)' -> LayerNorm -> Linear -> LayerNorm, + learned position embedding, dropout; the pad mask
+    all(patch == pad_token) is computed by the encoder itself."""
+    kind = "PatchEncoder"
 
     def __init__(self, patch_size=(16, 16), mode="matrix", num_channels=0, embedding_dim=512, max_tokens=1024,
                  dropout: float = 0.1, attn_mask=True, pad_token=-10000, **kwargs):
         super().__init__()
         assert mode in ["matrix", "image", "video"]
+        if mode != "matrix":
+            raise NotImplementedError("PatchEncoder modes 'image' / 'video' cannot run in the reference either "
+                                      "(encoders.py:252-259 never define self.layer used at :273)")
+        assert len(patch_size) == 2
         input_dim = 1
         for p in patch_size:
             input_dim *= p
-        if mode != "matrix":
-            input_dim *= num_channels
-        self.patch_size, self.mode, self.pad_token = patch_size, mode, -10000
+        self.patch_size, self.mode, self.pad_token = tuple(patch_size), mode, -10000  # encoders.py:234 ignores the argument
+        self.input_dim, self.max_tokens, self.p_drop, self.attn_mask = input_dim, max_tokens, float(dropout), attn_mask
         self.batch_to_tokens = nn.Sequential(nn.Identity(), nn.LayerNorm(input_dim), nn.Linear(input_dim, embedding_dim),
                                              nn.LayerNorm(embedding_dim))
         self.register_buffer("index", torch.arange(max_tokens))
         self.embedding = nn.Embedding(max_tokens, embedding_dim)
 
-    def forward(self, batch):
-        raise NotImplementedError("PatchEncoder has no sm_100a kernel yet (not used by any shipped config)")
+    def _spec(self):
+        return {"type": self.kind, "patch_size": self.patch_size, "max_tokens": self.max_tokens, "dropout": self.p_drop}
 
 
 encoders_dict = {

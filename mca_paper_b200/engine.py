@@ -171,8 +171,13 @@ class Engine:
                 kp = _round_up(kin, 64)
                 self.enc_kpad[name] = kp
                 add_matrix(pre + "proj", (D, kp), [(pre + "token_encoder.1.weight", D, kin, 0, 0, 0, 1.0)], self.B * L)
-            elif enc["type"] == "TabularEncoder":
+            elif enc["type"] in ("TabularEncoder", "SparseTabularEncoder"):
                 add_matrix(pre + "proj", (D, D), [(pre + "value_encoder.linear2.weight", D, D, 0, 0, 0, 1.0)], self.B * L)
+            elif enc["type"] == "PatchEncoder":
+                kin = int(np.prod(enc.get("patch_size", (16, 16))))
+                kp = _round_up(kin, 64)
+                self.enc_kpad[name] = kp
+                add_matrix(pre + "proj", (D, kp), [(pre + "batch_to_tokens.2.weight", D, kin, 0, 0, 0, 1.0)], self.B * L)
         self.arena = torch.zeros(a_off, device=dev, dtype=torch.bfloat16)
         self.garena = torch.zeros(g_off, device=dev, dtype=torch.float32)
         pd = np.zeros(len(rows), dtype=ops.PACK_DESC_DTYPE)
@@ -231,13 +236,22 @@ class Engine:
         ws["enc"] = {}
         for name, enc in zip(self.plan.names, self.model.encoder_specs):
             rows = B * enc["max_tokens"]
+            kind = enc["type"]
+            if kind == "SequenceEncoder":  # a table lookup: no projection workspace
+                ws["enc"][name] = {"flags": u8(int(enc.get("num_embeddings", 36602)))}
+                continue
             e = {"z": f32(rows, D), "st_out": f32(rows, 2)}
-            if enc["type"] == "EmbeddedSequenceEncoder":
+            if kind in ("EmbeddedSequenceEncoder", "PatchEncoder"):
                 kp = self.enc_kpad[name]
                 e.update(y=b16(rows, kp), st_in=f32(rows, 2), dz16=b16(rows, D), dz32=f32(rows, D), dy=f32(rows, kp))
+                if kind == "PatchEncoder":
+                    e.update(ptok=f32(rows, int(np.prod(enc.get("patch_size", (16, 16))))), mask=u8(B, enc["max_tokens"]))
             else:
                 e.update(h1=b16(rows, D), vpad=u8(rows), dz16=b16(rows, D), dz32=f32(rows, D), dh1=f32(rows, D))
+                if kind == "SparseTabularEncoder":
+                    e.update(flags=u8(int(enc.get("num_embeddings", 36602))))
             ws["enc"][name] = e
+        ws["drop_ctr"] = torch.zeros(1, device=dev, dtype=torch.int64)  # dropout counter: one tick per forward
         # loss
         nP = self.plan.n_pairs
         ws["losses"], ws["summary"], ws["w_default"] = f32(nP), f32(4), f32(nP)
@@ -336,7 +350,12 @@ class Engine:
     # ------------------------------------------------------------------------------------------ forward
     def build_offsets(self, batch):
         pl, ws = self.plan, self.ws
-        masks = [batch[n]["attention_mask"] for n in pl.names]
+        masks = []
+        for n, enc in zip(pl.names, self.model.encoder_specs):
+            if enc["type"] == "PatchEncoder":  # the encoder derives its own pad mask (encoders.py:273)
+                masks.append(self._patchify(n, enc, batch[n]["values"]))
+            else:
+                masks.append(batch[n]["attention_mask"])
         for m, L in zip(masks, pl.lengths):
             if m.shape != (self.B, L):
                 raise AssertionError(f"attention_mask shape {tuple(m.shape)} != {(self.B, L)} (batch must equal batch_size, model.py:454)")
@@ -349,6 +368,22 @@ class Engine:
              ctypes.cast(lens, ctypes.c_void_p), n, self.B, self.N, P(self.kt_start), P(self.kt_len), self.n_kt,
              P(ws["padding"]), P(ws["pad_mod"]), P(ws["present"]), P(ws["live_count"]), P(ws["live_idx"]),
              P(ws["cu_live"]), P(ws["kt_class"]), P(ws["kt_live"]), P(ws["any_absent"]), S())
+
+    def _patchify(self, name, enc, values):
+        """values [B,H,W] -> e['ptok'] [B*L, p1*p2] and the all-pad mask e['mask'] [B,L] (encoders.py:243-246,273)."""
+        e = self.ws["enc"][name]
+        if values.dtype != torch.float32 or not values.is_contiguous():
+            values = values.to(torch.float32).contiguous()
+        e["values"] = values
+        p1, p2 = (int(x) for x in enc.get("patch_size", (16, 16)))
+        Bv, Hh, Ww = values.shape
+        if Bv != self.B or (Hh // p1) * (Ww // p2) != enc["max_tokens"]:
+            raise AssertionError(f"{(Hh // p1) * (Ww // p2)} - {enc['max_tokens']}")  # encoders.py:270
+        call("mca_patchify", P(values), self.B, Hh, Ww, p1, p2, -10000.0, P(e["ptok"]), P(e["mask"]), S())
+        return e["mask"]
+
+    def _idx(self, t):
+        return t if (t.dtype == torch.int64 and t.is_contiguous()) else t.to(torch.int64).contiguous()
 
     def _pad_mod(self, i):
         pl = self.plan
@@ -395,10 +430,59 @@ class Engine:
                 ops.layernorm512_fwd(e["z"], self.pview(pre + "value_encoder.norm.weight"),
                                      self.pview(pre + "value_encoder.norm.bias"), x0, None, e["st_out"], rows,
                                      pad=e["vpad"], pe=emb, seg_len=L, out_rows_per_b=self.N, out_row_off=pl.offsets[i])
+            elif enc["type"] == "SequenceEncoder":
+                # encoders.py:161-166: Embedding(tokens) (looked-up rows renormalised in place) + sinusoidal PE
+                tok = e["idx"] = self._idx(batch[name]["tokens"])
+                emb = self.pview(pre + "token_encoder.embedding.weight")
+                V = emb.shape[0]
+                call("mca_embedding_renorm_indexed", P(emb), P(tok), rows, V, D, 1.0, P(e["flags"]), P(ws["nonfinite"]), S())
+                call("mca_embedding_gather", P(emb), P(tok), V, self.B, L, D,
+                     P(self.model.encoders[name].positional_encoder.pe), P(x0), self.N, pl.offsets[i], 0, S())
+            elif enc["type"] == "SparseTabularEncoder":
+                # encoders.py:114-120: Embedding(indices) + ContinuousValueEncoder(data)
+                idx = e["idx"] = self._idx(batch[name]["indices"])
+                vals = batch[name]["data"]
+                if vals.dtype != torch.float32 or not vals.is_contiguous():
+                    vals = vals.to(torch.float32).contiguous()
+                e["values"] = vals
+                emb = self.pview(pre + "token_encoder.embedding.weight")
+                V = emb.shape[0]
+                call("mca_embedding_renorm_indexed", P(emb), P(idx), rows, V, D, 1.0, P(e["flags"]), P(ws["nonfinite"]), S())
+                call("mca_tabular_fwd", P(vals), P(self.pview(pre + "value_encoder.linear1.weight")),
+                     P(self.pview(pre + "value_encoder.linear1.bias")), P(e["h1"]), P(e["vpad"]),
+                     float(enc.get("max_value", 10000)), float(enc.get("padding_idx", 0)), D, rows, S())
+                ops.gemm(e["h1"], 0, self.W(pre + "proj"), 0, rows, D, D, _lib.EPI_F32, e["z"],
+                         bias=self.pview(pre + "value_encoder.linear2.bias"))
+                ops.layernorm512_fwd(e["z"], self.pview(pre + "value_encoder.norm.weight"),
+                                     self.pview(pre + "value_encoder.norm.bias"), x0, None, e["st_out"], rows,
+                                     pad=e["vpad"], seg_len=L, out_rows_per_b=self.N, out_row_off=pl.offsets[i])
+                call("mca_embedding_gather", P(emb), P(idx), V, self.B, L, D, None, P(x0), self.N, pl.offsets[i], 1, S())
+            elif enc["type"] == "PatchEncoder":
+                # encoders.py:268-274: LN(in) -> Linear -> LN(512) of every patch (nothing is zeroed for padded patches),
+                # + learned position embedding, dropout in training mode; patches / mask were made by _patchify
+                kin, kp = e["ptok"].shape[1], self.enc_kpad[name]
+                call("mca_layernorm_in_fwd", P(e["ptok"]), P(self.pview(pre + "batch_to_tokens.1.weight")),
+                     P(self.pview(pre + "batch_to_tokens.1.bias")), None, P(e["y"]), P(e["st_in"]), kin, kp, rows,
+                     P(ws["nonfinite"]), S())
+                ops.gemm(e["y"], 0, self.W(pre + "proj"), 0, rows, D, kp, _lib.EPI_F32, e["z"],
+                         bias=self.pview(pre + "batch_to_tokens.2.bias"))
+                ops.layernorm512_fwd(e["z"], self.pview(pre + "batch_to_tokens.3.weight"),
+                                     self.pview(pre + "batch_to_tokens.3.bias"), x0, None, e["st_out"], rows,
+                                     pe=self.pview(pre + "embedding.weight"), seg_len=L, out_rows_per_b=self.N,
+                                     out_row_off=pl.offsets[i])
+                self._dropout(i, enc, x0)
             else:
-                raise NotImplementedError(f"{enc['type']} is not wired into the fused MCA path yet")
+                raise NotImplementedError(f"unknown encoder type {enc['type']}")
         if pl.F:
             call("mca_broadcast_rows", P(self.pview("fusion_tokens")), P(x0), pl.F, D, self.B, self.N, pl.n_tok, S())
+
+    def _dropout(self, i, enc, rows32):
+        """nn.Dropout of PatchEncoder (encoders.py:274) on the modality's rows of `rows32` (tokens in the forward, their
+        gradient in the backward: same counter -> same mask).  Inactive in eval mode, like the module."""
+        p = float(enc.get("dropout", 0.1))
+        if p > 0.0 and self.model.training:
+            call("mca_dropout_rows", P(rows32), self.B, enc["max_tokens"], D, self.N, self.plan.offsets[i], p,
+                 (torch.initial_seed() + 977 * i) & 0xFFFFFFFFFFFFFFFF, P(self.ws["drop_ctr"]), S())
 
     def attention_fwd(self, qkv, out, lse):
         ws = self.ws
@@ -410,6 +494,7 @@ class Engine:
         """encoders -> depth x [LN, QKV, attention, out-proj(+res), LN, FF1(GEGLU), FF2(+res)] -> LN -> pooling."""
         ws, M, IP = self.ws, self.M, self.IP
         ws["nonfinite"].zero_()
+        ws["drop_ctr"].add_(1)
         self.build_offsets(batch)
         self.encode(batch)
         # Residual wiring of model.py:117-122 (quirk Q1): x1 = LN(x); x2 = attn(x1) + x1; x3 = LN(x2); x' = ff(x3) + x3,
@@ -583,7 +668,27 @@ class Engine:
                 call("mca_layernorm_in_param_bwd", P(e["dy"]), kp, P(e["tokens"]), P(e["st_in"]), P(pad),
                      P(self.gview(pre + "token_encoder.0.weight")), P(self.gview(pre + "token_encoder.0.bias")), kin,
                      rows, S())
-            elif enc["type"] == "TabularEncoder":
+            elif enc["type"] == "SequenceEncoder":
+                emb = self.pview(pre + "token_encoder.embedding.weight")
+                call("mca_embedding_scatter_add", P(dx0), P(e["idx"]), emb.shape[0], self.B, L, D, self.N, pl.offsets[i],
+                     int(enc.get("padding_idx", 0)) % emb.shape[0], P(self.gview(pre + "token_encoder.embedding.weight")), S())
+            elif enc["type"] == "PatchEncoder":
+                kin, kp = e["ptok"].shape[1], self.enc_kpad[name]
+                self._dropout(i, enc, dx0)
+                call("mca_batchsum_rows", P(dx0), P(self.gview(pre + "embedding.weight")), L, D, self.B, self.N,
+                     pl.offsets[i], 1, S())
+                ops.layernorm512_bwd(dx0, e["z"], e["st_out"], self.pview(pre + "batch_to_tokens.3.weight"), e["dz32"],
+                                     e["dz16"], self.gview(pre + "batch_to_tokens.3.weight"),
+                                     self.gview(pre + "batch_to_tokens.3.bias"), rows, seg_len=L,
+                                     out_rows_per_b=self.N, out_row_off=pl.offsets[i])
+                call("mca_colsum", P(e["dz32"]), D, P(self.gview(pre + "batch_to_tokens.2.bias")), D, rows, S())
+                self._dw(pre + "proj", e["dz16"], e["y"], D, kp, rows)
+                ops.gemm(e["dz16"], 0, self.W(pre + "proj"), 1, rows, kp, D, _lib.EPI_F32, e["dy"])
+                call("mca_layernorm_in_param_bwd", P(e["dy"]), kp, P(e["ptok"]), P(e["st_in"]), None,
+                     P(self.gview(pre + "batch_to_tokens.1.weight")), P(self.gview(pre + "batch_to_tokens.1.bias")), kin,
+                     rows, S())
+            elif enc["type"] in ("TabularEncoder", "SparseTabularEncoder"):
+                sparse = enc["type"] == "SparseTabularEncoder"
                 ops.layernorm512_bwd(dx0, e["z"], e["st_out"], self.pview(pre + "value_encoder.norm.weight"), e["dz32"],
                                      e["dz16"], self.gview(pre + "value_encoder.norm.weight"),
                                      self.gview(pre + "value_encoder.norm.bias"), rows, pad=e["vpad"], seg_len=L,
@@ -596,8 +701,12 @@ class Engine:
                      P(self.gview(pre + "value_encoder.linear1.weight")), P(self.gview(pre + "value_encoder.linear1.bias")),
                      None, None, float(enc.get("max_value", 10000)), float(enc.get("padding_idx", -1)), D, rows, S())
                 gemb = self.gview(pre + "token_encoder.embedding.weight")
-                call("mca_batchsum_rows", P(dx0), P(gemb), L, D, self.B, self.N, pl.offsets[i], 1, S())
-                gemb[int(enc.get("padding_idx", -1)) % L].zero_()  # nn.Embedding padding_idx row gets no gradient
+                if sparse:
+                    call("mca_embedding_scatter_add", P(dx0), P(e["idx"]), gemb.shape[0], self.B, L, D, self.N,
+                         pl.offsets[i], int(enc.get("padding_idx", 0)) % gemb.shape[0], P(gemb), S())
+                else:
+                    call("mca_batchsum_rows", P(dx0), P(gemb), L, D, self.B, self.N, pl.offsets[i], 1, S())
+                    gemb[int(enc.get("padding_idx", -1)) % L].zero_()  # nn.Embedding padding_idx row gets no gradient
 
     # ------------------------------------------------------------------------------------------ optimiser
     def configure_optimizer(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=2.0,

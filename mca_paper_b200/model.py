@@ -210,8 +210,12 @@ class MCA(nn.Module):
         params = [p for _, p in eng._param_list()]
         want_loss = not no_loss
         pooled, losses, summary = _MCAFunction.apply(self, batch, want_loss, *params)
-        if self.check_finite and int(eng.ws["nonfinite"].item()) != 0:
-            raise Exception("Tokens are not finite")  # encoders.py:197-198
+        if self.check_finite:
+            flag = int(eng.ws["nonfinite"].item())
+            if flag & 2:
+                raise IndexError("index out of range in self")  # what nn.Embedding raises for a bad token / index
+            if flag & 1:
+                raise Exception("Tokens are not finite")  # encoders.py:197-198
         out = self._named_outputs(pooled)
         present = eng.ws["present"].clone().to(torch.bool)
         sample_mask = {name: present[:, i] for i, name in enumerate(self.modality_types)}

@@ -54,6 +54,11 @@ _SIGS = {
     "mca_dp_adamw_shard": [VP, I32, I32, VP, VP, VP, I64, I64, VP, VP, VP, F32, VP, VP],
     "mca_p2p_reduce_rows": [VP, I64, VP, I64, I32, VP],
     "mca_clip_adamw_step": [VP, VP, VP, VP, I64, VP, VP, VP, F32, VP, VP],
+    "mca_embedding_renorm_indexed": [VP, VP, I64, I32, I32, F32, VP, VP, VP],
+    "mca_embedding_gather": [VP, VP, I32, I32, I32, I32, VP, VP, I32, I32, I32, VP],
+    "mca_embedding_scatter_add": [VP, VP, I32, I32, I32, I32, I32, I32, I32, VP, VP],
+    "mca_patchify": [VP, I32, I32, I32, I32, I32, F32, VP, VP, VP],
+    "mca_dropout_rows": [VP, I32, I32, I32, I32, I32, F32, C.c_uint64, VP, VP],
     "mca_tabular_fwd": [VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_tabular_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_embedding_renorm": [VP, I32, I32, F32, VP],
@@ -86,7 +91,8 @@ def S():
 
 # kernels launched by each entry point (memsets not counted) — bench.py reports the per-step total
 KERNELS_PER_CALL = {"mca_build_offsets": 2, "mca_attn_fwd": 2, "mca_attn_bwd": 3, "mca_pool_attn_bwd": 2,
-                    "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3, "mca_dp_adamw_shard": 2}
+                    "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3, "mca_dp_adamw_shard": 2,
+                    "mca_embedding_renorm_indexed": 2}
 COUNT = {"n": 0}
 PROFILE = {"on": False, "events": []}
 RECORD = {"on": False, "calls": []}  # (name, tag, args) of every entry-point call, for isolated device timing

@@ -47,6 +47,36 @@ def make_batch(config, seed: int = 1, variant: str = "full", batch_size: int | N
                     if torch.rand(1, generator=g).item() < p:
                         values[b] = PAD_VALUE
             batch[name] = {"values": values, "attention_mask": (values == PAD_VALUE).to(torch.long)}
+        elif kind in ("SequenceEncoder", "SparseTabularEncoder"):
+            # SequenceCollator encoders.py:286-311: suffix padding with pad_token 0, attention_mask = (index == 0)
+            V = int(enc["num_embeddings"])
+            idx = torch.randint(1, V, (B, L), generator=g)
+            n_live = torch.full((B,), L, dtype=torch.long)
+            if variant != "full":
+                p = 0.3 if p_absent is None else p_absent
+                for b in range(B):
+                    n_live[b] = 0 if torch.rand(1, generator=g).item() < p else int(torch.randint(1, L + 1, (1,), generator=g))
+            live = torch.arange(L).unsqueeze(0) < n_live.unsqueeze(1)
+            idx = idx * live
+            mask = (idx == 0).to(torch.long)
+            if kind == "SequenceEncoder":
+                batch[name] = {"tokens": idx, "attention_mask": mask}
+            else:
+                data = torch.randn(B, L, generator=g) * live  # padded with 0.0 (encoders.py:308-309)
+                batch[name] = {"indices": idx, "data": data, "attention_mask": mask}
+        elif kind == "PatchEncoder":
+            # MatrixCollator layout: {'values': f32 [B,H,W]}; absent / padded regions hold pad_token -10000
+            Hh, Ww = int(enc["height"]), int(enc["width"])
+            values = torch.randn(B, Hh, Ww, generator=g)
+            if variant != "full":
+                p = 0.3 if p_absent is None else p_absent
+                for b in range(B):
+                    if torch.rand(1, generator=g).item() < p:
+                        values[b] = PAD_VALUE
+                    else:
+                        w_live = int(torch.randint(1, Ww + 1, (1,), generator=g))
+                        values[b, :, w_live:] = PAD_VALUE
+            batch[name] = {"values": values}
         else:
             raise NotImplementedError(kind)
     return batch
@@ -59,6 +89,8 @@ def batch_to(batch, device, non_blocking: bool = False):
 def live_token_fraction(batch, n_fusion: int) -> float:
     live = total = 0
     for d in batch.values():
+        if "attention_mask" not in d:
+            continue
         m = d["attention_mask"].to(torch.bool)
         live += int((~m).sum())
         total += m.numel()

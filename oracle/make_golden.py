@@ -32,6 +32,8 @@ CASES = {
     "tiny_cmu_fcl_ragged": dict(cfg=("cmu", dict(fcl=True)), variant="dropout_ragged", seed=1),
     "tiny_cmu_mma_absent": dict(cfg=("cmu", dict(zorro=True, fcl=False)), variant="dropout_full", seed=2),
     "tiny_tcga_all_losses": dict(cfg=("tcga", dict(fcl=True, bimodal=True, non_fusion_fcl=True)), variant="tcga", seed=1),
+    # SequenceEncoder + SparseTabularEncoder + PatchEncoder + EmbeddedSequenceEncoder, ragged / absent modalities
+    "tiny_mixed_encoders": dict(cfg=("mixed", dict(fcl=True)), variant="dropout_ragged", seed=3),
 }
 FULL_GRADS = ["return_tokens", "fusion_tokens", "norm.gamma", "layers.0.norm.gamma", "loss.loss_fn.logit_scale",
               "layers.1.norm.gamma"]

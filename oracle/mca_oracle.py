@@ -151,6 +151,58 @@ def tabular_encode(sd: dict, prefix: str, data: dict, max_value: float, padding_
     return x_t.unsqueeze(0) + h, data["attention_mask"]
 
 
+def _lookup_with_renorm(emb: torch.Tensor, idx: torch.Tensor, padding_idx: int, renorm_in_place: bool = True):
+    """nn.Embedding(padding_idx, max_norm=1.0) (encoders.py:31-37): the rows that are looked up are renormalised IN
+    PLACE (no gradient through the renorm), the padding_idx row receives no gradient."""
+    with torch.no_grad():
+        used = torch.unique(idx)
+        norms = emb[used].norm(dim=1, keepdim=True)
+        scale = torch.where(norms > 1.0, 1.0 / (norms + 1e-7), torch.ones_like(norms))
+        if renorm_in_place:
+            emb[used] = emb[used] * scale
+    n_rows = emb.shape[0]
+    keep = torch.ones(n_rows, 1, dtype=emb.dtype)
+    keep[padding_idx % n_rows] = 0.0
+    table = emb * keep + (emb * (1.0 - keep)).detach()
+    return table[idx]
+
+
+def sequence_encode(sd: dict, prefix: str, data: dict, padding_idx: int = 0):
+    """SequenceEncoder.forward encoders.py:161-166: Embedding(tokens) + sinusoidal PE at every position."""
+    tokens = data["tokens"].long()
+    x_t = _lookup_with_renorm(sd[prefix + "token_encoder.embedding.weight"], tokens, padding_idx)
+    pe = sd[prefix + "positional_encoder.pe"][: tokens.shape[1]]
+    return x_t + pe.unsqueeze(0), data["attention_mask"]
+
+
+def sparse_tabular_encode(sd: dict, prefix: str, data: dict, max_value: float, padding_idx: int = 0):
+    """SparseTabularEncoder.forward encoders.py:114-120: Embedding(indices) + ContinuousValueEncoder(data), whose pad
+    test is `data == padding_idx` (encoders.py:112 passes padding_idx as padding_value)."""
+    x_t = _lookup_with_renorm(sd[prefix + "token_encoder.embedding.weight"], data["indices"].long(), padding_idx)
+    v = data["data"].unsqueeze(-1)
+    pad = v == float(padding_idx)
+    v = torch.clamp(v, max=max_value)
+    h = torch.relu(F.linear(v, sd[prefix + "value_encoder.linear1.weight"], sd[prefix + "value_encoder.linear1.bias"]))
+    h = F.linear(h, sd[prefix + "value_encoder.linear2.weight"], sd[prefix + "value_encoder.linear2.bias"])
+    h = F.layer_norm(h, (h.shape[-1],), sd[prefix + "value_encoder.norm.weight"], sd[prefix + "value_encoder.norm.bias"])
+    return x_t + h.masked_fill(pad, 0.0), data["attention_mask"]
+
+
+def patch_encode(sd: dict, prefix: str, data: dict, patch_size, pad_token: float = -10000.0):
+    """PatchEncoder.forward encoders.py:268-274 in "matrix" mode, dropout inactive (eval mode or p = 0):
+    'b (h p1) (w p2) -> b (h w) (p1 p2)', LN -> Linear -> LN, + learned position embedding; mask = all(patch == pad)."""
+    v = data["values"]
+    p1, p2 = patch_size
+    Bv, Hh, Ww = v.shape
+    patches = v.view(Bv, Hh // p1, p1, Ww // p2, p2).permute(0, 1, 3, 2, 4).reshape(Bv, (Hh // p1) * (Ww // p2), p1 * p2)
+    x = F.layer_norm(patches, (p1 * p2,), sd[prefix + "batch_to_tokens.1.weight"], sd[prefix + "batch_to_tokens.1.bias"])
+    x = F.linear(x, sd[prefix + "batch_to_tokens.2.weight"], sd[prefix + "batch_to_tokens.2.bias"])
+    x = F.layer_norm(x, (x.shape[-1],), sd[prefix + "batch_to_tokens.3.weight"], sd[prefix + "batch_to_tokens.3.bias"])
+    x = x + sd[prefix + "embedding.weight"][: x.shape[1]].unsqueeze(0)
+    mask = torch.all(patches == pad_token, dim=-1).to(torch.long)
+    return x, mask
+
+
 def encode_modality(sd: dict, name: str, cfg: dict, data: dict):
     kind = cfg["type"]
     prefix = f"encoders.{name}."
@@ -159,6 +211,12 @@ def encode_modality(sd: dict, name: str, cfg: dict, data: dict):
     if kind == "TabularEncoder":
         # encoders.py:77-88: padding_idx default -1 is forwarded to the value encoder as its padding_value
         return tabular_encode(sd, prefix, data, float(cfg.get("max_value", 10000)), float(cfg.get("padding_idx", -1)))
+    if kind == "SequenceEncoder":
+        return sequence_encode(sd, prefix, data, int(cfg.get("padding_idx", 0)))
+    if kind == "SparseTabularEncoder":
+        return sparse_tabular_encode(sd, prefix, data, float(cfg.get("max_value", 10000)), int(cfg.get("padding_idx", 0)))
+    if kind == "PatchEncoder":
+        return patch_encode(sd, prefix, data, tuple(cfg.get("patch_size", (16, 16))))
     raise NotImplementedError(kind)
 
 

@@ -274,6 +274,54 @@ def test_column_reductions():
     assert rel_err(out, a.sum(0)) < 1e-5
 
 
+# ------------------------------------------------------------------------------------------------ index encoders
+def test_embedding_renorm_gather_scatter():
+    """nn.Embedding(max_norm=1, padding_idx) pieces of SequenceEncoder / SparseTabularEncoder against torch."""
+    torch.manual_seed(5)
+    V, B, Lq, d, N, off = 60, 4, 24, 512, 40, 7
+    emb = torch.randn(V, d, device=dev) * 0.06          # row norms around 1.36 -> most get renormalised
+    emb[3] *= 0.1                                       # one row below max_norm stays untouched
+    idx = torch.randint(0, 20, (B, Lq), device=dev)     # rows 20.. are never looked up -> never renormalised
+    ref_mod = torch.nn.Embedding(V, d, padding_idx=0, max_norm=1.0).to(dev)
+    with torch.no_grad():
+        ref_mod.weight.copy_(emb)
+    out_ref = ref_mod(idx)
+    flags = torch.zeros(V, device=dev, dtype=torch.uint8)
+    bad = torch.zeros(1, device=dev, dtype=torch.int32)
+    call("mca_embedding_renorm_indexed", P(emb), P(idx), B * Lq, V, d, 1.0, P(flags), P(bad), stream())
+    assert rel_err(emb, ref_mod.weight) < 1e-6 and int(flags.sum()) == 0 and int(bad.item()) == 0
+    pe = torch.randn(Lq, d, device=dev)
+    dst = torch.zeros(B * N, d, device=dev)
+    call("mca_embedding_gather", P(emb), P(idx), V, B, Lq, d, P(pe), P(dst), N, off, 0, stream())
+    got = dst.view(B, N, d)[:, off:off + Lq]
+    assert rel_err(got, out_ref + pe) < 1e-6
+    call("mca_embedding_gather", P(emb), P(idx), V, B, Lq, d, None, P(dst), N, off, 1, stream())      # accumulate form
+    assert rel_err(dst.view(B, N, d)[:, off:off + Lq], 2 * out_ref + pe) < 1e-6
+    dsrc = torch.randn(B * N, d, device=dev)
+    out_ref.backward(dsrc.view(B, N, d)[:, off:off + Lq])
+    demb = torch.zeros(V, d, device=dev)
+    call("mca_embedding_scatter_add", P(dsrc), P(idx), V, B, Lq, d, N, off, 0, P(demb), stream())
+    assert rel_err(demb, ref_mod.weight.grad) < 1e-5 and float(demb[0].abs().max()) == 0.0             # padding row
+    idx[1, 2] = V + 5                                                                                   # out of range
+    call("mca_embedding_renorm_indexed", P(emb), P(idx), B * Lq, V, d, 1.0, P(flags), P(bad), stream())
+    assert int(bad.item()) == 2
+
+
+def test_patchify_bit_exact():
+    torch.manual_seed(6)
+    B, Hh, Ww, p1, p2 = 3, 16, 48, 4, 8
+    v = torch.randn(B, Hh, Ww, device=dev)
+    v[1, :, 24:] = -10000.0
+    v[2] = -10000.0
+    L = (Hh // p1) * (Ww // p2)
+    tok = torch.zeros(B * L, p1 * p2, device=dev)
+    mask = torch.zeros(B, L, device=dev, dtype=torch.uint8)
+    call("mca_patchify", P(v), B, Hh, Ww, p1, p2, -10000.0, P(tok), P(mask), stream())
+    want = v.view(B, Hh // p1, p1, Ww // p2, p2).permute(0, 1, 3, 2, 4).reshape(B, L, p1 * p2)   # 'b (h p1) (w p2) -> b (h w) (p1 p2)'
+    assert torch.equal(tok.view(B, L, -1), want)
+    assert torch.equal(mask.bool(), (want == -10000.0).all(-1))
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _attention_case(cfg, variant, scale):
     kw = C.get_model_config(cfg)
