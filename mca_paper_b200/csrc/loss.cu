@@ -1,4 +1,4 @@
-// All-pairs temperature-scaled InfoNCE, forward and analytic backward, one CTA per contrastive pair.
+// All-pairs temperature-scaled InfoNCE, forward and analytic backward, one CTA per (contrastive pair, direction).
 // Replaces the Python loop MCAPretrainingLoss.forward (model.py:196-232) and, per pair,
 // ContrastiveLossWithTemperature (utils/contrastive_loss_with_temperature.py:71-100,187): in-place clamp of
 // logit_scale, T = exp(s), logits_a = a b_all^T T, logits_b = b a_all^T T, rows selected by the presence mask,
@@ -57,99 +57,130 @@ __device__ __forceinline__ bool row_selected(const LossArgs& a, const mca_loss_p
   return true;
 }
 
-// logits into smem: la[i*GB + j], lb[i*GB + j]
-__device__ void compute_logits(const LossArgs& a, const mca_loss_pair& p, float T, float* la, float* lb) {
+// One CTA = one (pair, direction): direction 0 scores the local a rows against every gathered b row, direction 1 the
+// local b rows against every gathered a row.  The B local query rows are staged in shared memory once; each warp then
+// reads a gathered key row ONCE (coalesced float4) and dots it with all B queries, so the global traffic is GB rows per
+// CTA, not B*GB.  logits[i*GB + j] = T * q_i . k_j
+constexpr int LOSS_MAXB = 16;  // local batch rows held in registers by the backward
+
+__device__ void stage_and_logits(const LossArgs& a, const mca_loss_pair& p, int dir, float T, float* qs, float* lg) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int total = 2 * a.B * a.GB;
-  for (int t = warp; t < total; t += nwarps) {
-    const int dir = t / (a.B * a.GB);
-    const int i = (t / a.GB) % a.B, j = t % a.GB;
-    const int rq = dir == 0 ? p.a_row : p.b_row, rk = dir == 0 ? p.b_row : p.a_row;
-    const float* q = pooled_row(a, a.rank * a.B + i, rq);
-    const float* k = pooled_row(a, j, rk);
-    float acc = 0.f;
-    for (int c = lane * 4; c < a.d; c += 128) {
-      const float4 x = *reinterpret_cast<const float4*>(q + c);
-      const float4 y = *reinterpret_cast<const float4*>(k + c);
-      acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
-    }
-    acc = warp_sum_f(acc);
-    if (lane == 0) (dir == 0 ? la : lb)[i * a.GB + j] = acc * T;
+  const int rq = dir == 0 ? p.a_row : p.b_row, rk = dir == 0 ? p.b_row : p.a_row;
+  const int d4 = a.d / 4;
+  for (int t = threadIdx.x; t < a.B * d4; t += blockDim.x) {
+    const int i = t / d4, c = t % d4;
+    reinterpret_cast<float4*>(qs)[t] = reinterpret_cast<const float4*>(pooled_row(a, a.rank * a.B + i, rq))[c];
   }
+  __syncthreads();
+  for (int j = warp; j < a.GB; j += nwarps) {
+    const float4* k4 = reinterpret_cast<const float4*>(pooled_row(a, j, rk));
+    float acc[LOSS_MAXB];
+#pragma unroll
+    for (int i = 0; i < LOSS_MAXB; ++i) acc[i] = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 y = k4[c];
+#pragma unroll
+      for (int i = 0; i < LOSS_MAXB; ++i) {
+        if (i < a.B) {
+          const float4 x = reinterpret_cast<const float4*>(qs)[i * d4 + c];
+          acc[i] += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LOSS_MAXB; ++i) {
+      if (i < a.B) {
+        const float v = warp_sum_f(acc[i]);
+        if (lane == 0) lg[i * a.GB + j] = v * T;
+      }
+    }
+  }
+  __syncthreads();
 }
 
 __global__ void clamp_scale_kernel(float* s, float lo, float hi) {
   if (threadIdx.x == 0) *s = fminf(fmaxf(*s, lo), hi);
 }
 
+// sum0[pair] (direction 0) / sum1[pair] (direction 1) = sum of the selected rows' cross entropies; the caller passes the
+// `losses` and `w_default` outputs as the two scratch arrays, loss_reduce_kernel finishes them
 __global__ void __launch_bounds__(LOSS_THREADS)
-loss_fwd_kernel(LossArgs a, float* __restrict__ losses) {
-  extern __shared__ float sm[];
-  float* la = sm;
-  float* lb = sm + a.B * a.GB;
-  __shared__ float s_sum[2];
-  __shared__ int s_cnt;
-  const mca_loss_pair p = a.plan[blockIdx.x];
+loss_fwd_kernel(LossArgs a, float* __restrict__ sum0, float* __restrict__ sum1) {
+  extern __shared__ __align__(16) float sm[];
+  float* qs = sm;
+  float* lg = sm + a.B * a.d;
+  __shared__ float s_sum;
+  const int pair = blockIdx.x, dir = blockIdx.y;
+  const mca_loss_pair p = a.plan[pair];
   const float T = expf(*a.logit_scale);
-  if (threadIdx.x == 0) s_sum[0] = 0.f, s_sum[1] = 0.f, s_cnt = 0;
-  compute_logits(a, p, T, la, lb);
-  __syncthreads();
+  if (threadIdx.x == 0) s_sum = 0.f;
+  stage_and_logits(a, p, dir, T, qs, lg);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int t = warp; t < 2 * a.B; t += nwarps) {
-    const int dir = t / a.B, i = t % a.B;
+  for (int i = warp; i < a.B; i += nwarps) {
     if (!row_selected(a, p, i)) continue;
-    const float* row = (dir == 0 ? la : lb) + i * a.GB;
+    const float* row = lg + i * a.GB;
     float mx = -CUDART_INF_F;
     for (int j = lane; j < a.GB; j += 32) mx = fmaxf(mx, row[j]);
     mx = warp_max_f(mx);
     float se = 0.f;
     for (int j = lane; j < a.GB; j += 32) se += expf(row[j] - mx);
     se = warp_sum_f(se);
-    if (lane == 0) {
-      const float ce = mx + logf(se) - row[a.rank * a.B + i];
-      atomicAdd(&s_sum[dir], ce);
-      if (dir == 0) atomicAdd(&s_cnt, 1);
-    }
+    if (lane == 0) atomicAdd(&s_sum, mx + logf(se) - row[a.rank * a.B + i]);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    losses[blockIdx.x] = s_cnt == 0 ? CUDART_NAN_F : 0.5f * (s_sum[0] + s_sum[1]) / static_cast<float>(s_cnt);
-  }
+  if (threadIdx.x == 0) (dir == 0 ? sum0 : sum1)[pair] = s_sum;
 }
 
+// losses[p] = (CE_a + CE_b) / 2 averaged over the selected rows, NaN when no row is selected;
 // summary[0] = loss (model.py:224-232), [1] = fcl_loss, [2] = no-fcl_loss (model.py:221-222), [3] = #non-NaN;
 // w_default[p] = d loss / d loss_p
-__global__ void loss_reduce_kernel(const float* __restrict__ losses, const mca_loss_pair* __restrict__ plan, int P,
-                                   float* __restrict__ summary, float* __restrict__ w_default) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float tot = 0.f, fcl = 0.f, nofcl = 0.f;
-  int nv = 0, nf = 0, nn = 0;
-  for (int p = 0; p < P; ++p) {
-    float v = losses[p];
-    const bool isn = isnan(v);
-    if (!isn) ++nv;
-    if (isn) v = 0.f;
-    else if (isinf(v)) v = v > 0 ? 3.402823466e+38f : -3.402823466e+38f;
-    tot += v;
-    if (plan[p].is_fcl) fcl += v, ++nf;
-    else nofcl += v, ++nn;
+__global__ void __launch_bounds__(256)
+loss_reduce_kernel(LossArgs a, float* __restrict__ losses, int P, float* __restrict__ summary,
+                   float* __restrict__ w_default) {
+  const mca_loss_pair* plan = a.plan;
+  // thread = pair: selected-row count and the pair's loss from the two direction sums
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    int cnt = 0;
+    for (int i = 0; i < a.B; ++i) cnt += row_selected(a, plan[p], i) ? 1 : 0;
+    losses[p] = cnt == 0 ? CUDART_NAN_F : 0.5f * (losses[p] + w_default[p]) / static_cast<float>(cnt);
   }
-  summary[0] = nv == 0 ? tot : tot / static_cast<float>(nv);
-  summary[1] = nf > 0 ? fcl / nf : 0.f;
-  summary[2] = nn > 0 ? nofcl / nn : 0.f;
-  summary[3] = static_cast<float>(nv);
-  for (int p = 0; p < P; ++p) w_default[p] = (isnan(losses[p]) || nv == 0) ? 0.f : 1.0f / static_cast<float>(nv);
+  __syncthreads();
+  __shared__ int s_nv;
+  if (threadIdx.x == 0) {
+    float tot = 0.f, fcl = 0.f, nofcl = 0.f;
+    int nv = 0, nf = 0, nn = 0;
+    for (int p = 0; p < P; ++p) {
+      float v = losses[p];
+      const bool isn = isnan(v);
+      if (!isn) ++nv;
+      if (isn) v = 0.f;
+      else if (isinf(v)) v = v > 0 ? 3.402823466e+38f : -3.402823466e+38f;
+      tot += v;
+      if (plan[p].is_fcl) fcl += v, ++nf;
+      else nofcl += v, ++nn;
+    }
+    summary[0] = nv == 0 ? tot : tot / static_cast<float>(nv);
+    summary[1] = nf > 0 ? fcl / nf : 0.f;
+    summary[2] = nn > 0 ? nofcl / nn : 0.f;
+    summary[3] = static_cast<float>(nv);
+    s_nv = nv;
+  }
+  __syncthreads();
+  const int nv = s_nv;
+  for (int p = threadIdx.x; p < P; p += blockDim.x)
+    w_default[p] = (isnan(losses[p]) || nv == 0) ? 0.f : 1.0f / static_cast<float>(nv);
 }
 
 __global__ void __launch_bounds__(LOSS_THREADS)
 loss_bwd_kernel(LossArgs a, const float* __restrict__ w, float* __restrict__ dpooled_all, float* __restrict__ dscale) {
-  extern __shared__ float sm[];
-  float* la = sm;
-  float* lb = sm + a.B * a.GB;
+  extern __shared__ __align__(16) float sm[];
+  float* qs = sm;
+  float* lg = sm + a.B * a.d;
   __shared__ int s_cnt;
   __shared__ float s_ds;
-  const mca_loss_pair p = a.plan[blockIdx.x];
-  const float wp = w[blockIdx.x];
+  const int pair = blockIdx.x, dir = blockIdx.y;
+  const mca_loss_pair p = a.plan[pair];
+  const float wp = w[pair];
   if (wp == 0.f) return;
   const float T = expf(*a.logit_scale);
   if (threadIdx.x == 0) {
@@ -158,15 +189,13 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ w, float* __restrict__ dpo
     s_cnt = c;
     s_ds = 0.f;
   }
-  compute_logits(a, p, T, la, lb);
-  __syncthreads();
+  stage_and_logits(a, p, dir, T, qs, lg);
   if (s_cnt == 0) return;
   const float gscale = wp * 0.5f / static_cast<float>(s_cnt);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   // logits -> dL/dlogits in place; accumulate dL/ds = sum dlogit * logit
-  for (int t = warp; t < 2 * a.B; t += nwarps) {
-    const int dir = t / a.B, i = t % a.B;
-    float* row = (dir == 0 ? la : lb) + i * a.GB;
+  for (int i = warp; i < a.B; i += nwarps) {
+    float* row = lg + i * a.GB;
     if (!row_selected(a, p, i)) {
       for (int j = lane; j < a.GB; j += 32) row[j] = 0.f;
       continue;
@@ -190,25 +219,30 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ w, float* __restrict__ dpo
   }
   __syncthreads();
   if (threadIdx.x == 0) atomicAdd(dscale, s_ds);
-  // embedding gradients. dir 0: logits_a[i][j] = T a_i . b_all[j];  dir 1: logits_b[i][j] = T b_i . a_all[j]
+  // embedding gradients, thread = embedding column: d query_i += T sum_j dl[i][j] key_j ; d key_j += T sum_i dl[i][j] query_i.
+  // Every gathered key row is read once per CTA (coalesced across the threads).
+  const int rq = dir == 0 ? p.a_row : p.b_row, rk = dir == 0 ? p.b_row : p.a_row;
   for (int c = threadIdx.x; c < a.d; c += blockDim.x) {
-    for (int dir = 0; dir < 2; ++dir) {
-      const float* dl = dir == 0 ? la : lb;
-      const int rq = dir == 0 ? p.a_row : p.b_row, rk = dir == 0 ? p.b_row : p.a_row;
-      // d query_i += T sum_j dl[i][j] key_all[j]
-      for (int i = 0; i < a.B; ++i) {
-        float acc = 0.f;
-        for (int j = 0; j < a.GB; ++j) acc += dl[i * a.GB + j] * pooled_row(a, j, rk)[c];
-        if (acc != 0.f)
-          atomicAdd(dpooled_all + (static_cast<long long>(a.rank * a.B + i) * a.R + rq) * a.d + c, T * acc);
+    float qreg[LOSS_MAXB], dq[LOSS_MAXB];
+#pragma unroll
+    for (int i = 0; i < LOSS_MAXB; ++i) qreg[i] = i < a.B ? qs[i * a.d + c] : 0.f, dq[i] = 0.f;
+    for (int j = 0; j < a.GB; ++j) {
+      const float k = pooled_row(a, j, rk)[c];
+      float dk = 0.f;
+#pragma unroll
+      for (int i = 0; i < LOSS_MAXB; ++i) {
+        if (i < a.B) {
+          const float g = lg[i * a.GB + j];
+          dq[i] += g * k;
+          dk += g * qreg[i];
+        }
       }
-      // d key_all[j] += T sum_i dl[i][j] query_i
-      for (int j = 0; j < a.GB; ++j) {
-        float acc = 0.f;
-        for (int i = 0; i < a.B; ++i) acc += dl[i * a.GB + j] * pooled_row(a, a.rank * a.B + i, rq)[c];
-        if (acc != 0.f) atomicAdd(dpooled_all + (static_cast<long long>(j) * a.R + rk) * a.d + c, T * acc);
-      }
+      if (dk != 0.f) atomicAdd(dpooled_all + (static_cast<long long>(j) * a.R + rk) * a.d + c, T * dk);
     }
+#pragma unroll
+    for (int i = 0; i < LOSS_MAXB; ++i)
+      if (i < a.B && dq[i] != 0.f)
+        atomicAdd(dpooled_all + (static_cast<long long>(a.rank * a.B + i) * a.R + rq) * a.d + c, T * dq[i]);
   }
 }
 
@@ -275,15 +309,15 @@ p2p_reduce_rows_kernel(const float* const* __restrict__ src_peers, long long off
 
 using namespace mca;
 
-static int loss_smem_bytes(int B, int GB) { return 2 * B * GB * static_cast<int>(sizeof(float)); }
+static int loss_smem_bytes(int B, int GB, int d) { return (B * d + B * GB) * static_cast<int>(sizeof(float)); }
 
 extern "C" int mca_contrastive_allpairs_fwd(const float* pooled_all, const uint8_t* present,
                                             const mca_loss_pair* plan_dev, int n_pairs, float* logit_scale, int B,
                                             int GB, int R, int d, int n_mod, int rank, float scale_min,
                                             float scale_max, float* losses, float* summary, float* w_default,
                                             void* stream_) {
-  if (n_pairs <= 0 || B <= 0 || GB < B || (d % 4) != 0 || n_mod > MCA_MAX_MODALITIES) return MCA_ERR_SHAPE;
-  const int smem = loss_smem_bytes(B, GB);
+  if (n_pairs <= 0 || B <= 0 || B > LOSS_MAXB || GB < B || (d % 4) != 0 || n_mod > MCA_MAX_MODALITIES) return MCA_ERR_SHAPE;
+  const int smem = loss_smem_bytes(B, GB, d);
   if (smem > 96 * 1024) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   static bool attr = false;
@@ -294,8 +328,8 @@ extern "C" int mca_contrastive_allpairs_fwd(const float* pooled_all, const uint8
   }
   clamp_scale_kernel<<<1, 32, 0, stream>>>(logit_scale, scale_min, scale_max);
   LossArgs a{pooled_all, present, plan_dev, logit_scale, B, GB, R, d, n_mod, rank, n_pairs};
-  loss_fwd_kernel<<<n_pairs, LOSS_THREADS, smem, stream>>>(a, losses);
-  loss_reduce_kernel<<<1, 32, 0, stream>>>(losses, plan_dev, n_pairs, summary, w_default);
+  loss_fwd_kernel<<<dim3(n_pairs, 2), LOSS_THREADS, smem, stream>>>(a, losses, w_default);
+  loss_reduce_kernel<<<1, 256, 0, stream>>>(a, losses, n_pairs, summary, w_default);
   return check_launch();
 }
 
@@ -303,8 +337,8 @@ extern "C" int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8
                                             const mca_loss_pair* plan_dev, int n_pairs, float* logit_scale, int B,
                                             int GB, int R, int d, int n_mod, int rank, const float* w,
                                             float* dpooled_all, float* dscale, void* stream_) {
-  if (n_pairs <= 0 || B <= 0 || GB < B || (d % 4) != 0) return MCA_ERR_SHAPE;
-  const int smem = loss_smem_bytes(B, GB);
+  if (n_pairs <= 0 || B <= 0 || B > LOSS_MAXB || GB < B || (d % 4) != 0) return MCA_ERR_SHAPE;
+  const int smem = loss_smem_bytes(B, GB, d);
   if (smem > 96 * 1024) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   static bool attr = false;
@@ -313,7 +347,7 @@ extern "C" int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8
     attr = true;
   }
   LossArgs a{pooled_all, present, plan_dev, logit_scale, B, GB, R, d, n_mod, rank, n_pairs};
-  loss_bwd_kernel<<<n_pairs, LOSS_THREADS, smem, stream>>>(a, w, dpooled_all, dscale);
+  loss_bwd_kernel<<<dim3(n_pairs, 2), LOSS_THREADS, smem, stream>>>(a, w, dpooled_all, dscale);
   return check_launch();
 }
 

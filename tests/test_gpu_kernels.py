@@ -282,14 +282,21 @@ def test_embedding_renorm_gather_scatter():
     emb = torch.randn(V, d, device=dev) * 0.06          # row norms around 1.36 -> most get renormalised
     emb[3] *= 0.1                                       # one row below max_norm stays untouched
     idx = torch.randint(0, 20, (B, Lq), device=dev)     # rows 20.. are never looked up -> never renormalised
-    ref_mod = torch.nn.Embedding(V, d, padding_idx=0, max_norm=1.0).to(dev)
-    with torch.no_grad():
-        ref_mod.weight.copy_(emb)
-    out_ref = ref_mod(idx)
+    # expected weights: every looked-up row renormalised ONCE (what the reference's CPU nn.Embedding does; torch's CUDA
+    # embedding_renorm_ races on duplicate indices and is itself off by 1-3 % in most runs, scripts/gpu_dbg_renorm.py)
+    want = emb.clone()
+    u = torch.unique(idx)
+    nrm = want[u].norm(dim=1, keepdim=True)
+    want[u] = torch.where(nrm > 1.0, want[u] * (1.0 / (nrm + 1e-7)), want[u])
     flags = torch.zeros(V, device=dev, dtype=torch.uint8)
     bad = torch.zeros(1, device=dev, dtype=torch.int32)
     call("mca_embedding_renorm_indexed", P(emb), P(idx), B * Lq, V, d, 1.0, P(flags), P(bad), stream())
-    assert rel_err(emb, ref_mod.weight) < 1e-6 and int(flags.sum()) == 0 and int(bad.item()) == 0
+    assert rel_err(emb, want) < 1e-6 and int(flags.sum()) == 0 and int(bad.item()) == 0
+    assert torch.equal(emb[20:], want[20:])             # untouched rows are bit-identical
+    ref_mod = torch.nn.Embedding(V, d, padding_idx=0).to(dev)   # lookups / gradients on the renormalised table
+    with torch.no_grad():
+        ref_mod.weight.copy_(emb)
+    out_ref = ref_mod(idx)
     pe = torch.randn(Lq, d, device=dev)
     dst = torch.zeros(B * N, d, device=dev)
     call("mca_embedding_gather", P(emb), P(idx), V, B, Lq, d, P(pe), P(dst), N, off, 0, stream())
