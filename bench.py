@@ -157,6 +157,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(entry_point: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the entry point's main kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by scripts/ncu_traffic.py); None when there is none."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(entry_point, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------- B200 arm
 def algorithmic_flops(plan, B, H, depth, I):
     """only mask-allowed (q,k) pairs at full length, 2 FLOP/MAC, backward = 2x forward."""
@@ -316,7 +327,7 @@ def main():
             dur = per_kernel[top]["us_avg"] * 1e-6
             ach = f / dur / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(tname),
                     "algorithmic_flops_per_launch": f, "avg_launch_us": per_kernel[top]["us_avg"],
                     "launches_per_step": per_kernel[top]["launches_per_step"],
                     "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
@@ -336,13 +347,16 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        bs = 2
+        bs, n_timed = 4, 2
         step = cpu_training_step_fn(args.config, bs)
+        step()  # warm-up (allocator, thread pool)
         t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
+        for _ in range(n_timed):
+            step()
+        dt = (time.perf_counter() - t0) / n_timed
         cpu_base = {"value": bs / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"1 CPU training step (fwd+bwd+clip+AdamW, fp32) on {bs} samples of the same shape, oracle/mca_oracle.py"}
+                    "sample": f"{n_timed} timed CPU training steps (fwd+bwd+clip+AdamW, fp32, after 1 warm-up) on {bs} samples of the "
+                              f"same shape, oracle/mca_oracle.py"}
 
     if rank == 0:
         value = world * B * args.steps / (ms_dev * 1e-3)
@@ -355,6 +369,8 @@ def main():
                                    f"GloVe 50x300, 88 fusion tokens -> N=2538, d=512, 5 layers, {eng.plan.n_pairs} InfoNCE pairs), "
                                    f"variant={args.variant}",
                        "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graphs": not args.no_graphs,
+                       "dp_exchange": ("none" if world == 1 else ("peer memory (push/pull kernels + flag barriers, one graph)"
+                                                                 if eng._p2p is not None else "nccl")),
                        "l2": "per-step working set (~2 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "precision": "bf16 tensor-core operands, fp32 accumulate, fp32 master weights/residual stream/LN/softmax/loss"},
             "clocks": clocks,

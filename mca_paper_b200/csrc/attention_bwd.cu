@@ -129,6 +129,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_init(sdq_full, 128);
     mbar_init(sdq_free, 1);
     fence_mbar_init();
+    // K / V and the first Q / dO tile are requested right away: their DRAM latency overlaps the TMEM allocation, the
+    // schedule staging and the constant-tile setup below instead of following the CTA-wide barrier
+    if (n_iter > 0) {
+      const int krow = static_cast<int>(row0 + KT.start);
+      mbar_expect_tx(kv_full, 2 * AB_TILE);
+      tma_load_2d(sK, &tm_qkv, kv_full, HD + h * AB_DH, krow);
+      tma_load_2d(sV, &tm_qkv, kv_full, 2 * HD + h * AB_DH, krow);
+      const int qrow = static_cast<int>(row0 + a.q_tiles[a.qt_list[KT.kt_off].tile].start);
+      mbar_expect_tx(&qdo_full[0], 2 * AB_TILE);
+      tma_load_2d(sQ, &tm_qkv, &qdo_full[0], h * AB_DH, qrow);
+      tma_load_2d(sdO, &tm_do, &qdo_full[0], h * AB_DH, qrow);
+    }
   }
   if (warp == 9) tmem_alloc(tmem_holder, 512);
   for (int i = threadIdx.x; i < n_iter; i += AB_THREADS) {
@@ -155,14 +167,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   if (warp == 8) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     if (n_iter > 0) {
-      const int krow = static_cast<int>(row0 + KT.start);
-      if (elect_one()) {
-        mbar_expect_tx(kv_full, 2 * AB_TILE);
-        tma_load_2d(sK, &tm_qkv, kv_full, HD + h * AB_DH, krow);
-        tma_load_2d(sV, &tm_qkv, kv_full, 2 * HD + h * AB_DH, krow);
-      }
-      __syncwarp();
-      for (int it = 0; it < n_iter; ++it) {
+      for (int it = 1; it < n_iter; ++it) {  // K / V and tile 0 were requested before the CTA-wide barrier
         const int s = it % AB_QSTAGES;
         const uint32_t sph = (it / AB_QSTAGES) & 1;
         const int qrow = static_cast<int>(row0 + s_qt[it].x);
@@ -367,11 +372,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       fence_proxy_async_smem();
       mbar_arrive(sdq_full);
     };
-    load_q(0);
-    write_ext(0);
-    load_q(1);
-    write_ext(1);
-    load_q(2);
+    {  // tiles 0 and 1: both sets of per-query loads in flight before either is consumed (one DRAM latency, not two)
+      load_q(0);
+      const float l0 = r_lse, d0 = r_dl;
+      const uint32_t b0 = r_rb;
+      load_q(1);
+      const float l1 = r_lse, d1 = r_dl;
+      const uint32_t b1 = r_rb;
+      r_lse = l0, r_dl = d0, r_rb = b0;
+      write_ext(0);
+      r_lse = l1, r_dl = d1, r_rb = b1;
+      write_ext(1);
+      load_q(2);
+    }
     mbar_arrive(x_free);  // phase 0: the B rows of tiles 0 and 1 are in place
     for (int t = 0; t < n_iter; ++t) {
       const uint32_t ph = t & 1;

@@ -64,7 +64,31 @@ clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
   const float coef = s_coef, lr = s_lr, bc1 = s_bc1, bc2s = s_bc2s;
   const float decay = 1.0f - lr * c.weight_decay;
   const float step_size = lr / bc1;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+  // float4 lanes: four independent 16-byte loads in flight per thread and iteration (the flat buffers are 256-byte
+  // aligned and their length is a multiple of 64 elements; a scalar tail keeps the kernel general)
+  const long long n4 = n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 gq = reinterpret_cast<const float4*>(g)[i];
+    float4 mq = reinterpret_cast<float4*>(m)[i];
+    float4 vq = reinterpret_cast<float4*>(v)[i];
+    float4 pq = reinterpret_cast<float4*>(p)[i];
+    const float gs[4] = {gq.x * coef, gq.y * coef, gq.z * coef, gq.w * coef};
+    float* mm = reinterpret_cast<float*>(&mq);
+    float* vv = reinterpret_cast<float*>(&vq);
+    float* pp = reinterpret_cast<float*>(&pq);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] = c.beta1 * mm[k] + (1.0f - c.beta1) * gs[k];
+      vv[k] = c.beta2 * vv[k] + (1.0f - c.beta2) * gs[k] * gs[k];
+      const float denom = sqrtf(vv[k]) / bc2s + c.eps;
+      pp[k] = pp[k] * decay - step_size * (mm[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pq;
+    reinterpret_cast<float4*>(m)[i] = mq;
+    reinterpret_cast<float4*>(v)[i] = vq;
+  }
+  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float gi = g[i] * coef;
     const float mi = c.beta1 * m[i] + (1.0f - c.beta1) * gi;
