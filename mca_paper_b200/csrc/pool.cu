@@ -161,7 +161,9 @@ pool_fwd_cl_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict
   float* xsum = xmax + PC * PR;        // [PC][16] row sums
   float* part = xsum + PC * PR;        // [4][16][64]
   float* xpart = part + 4 * PR * DH;   // [PC][16][64] partial outputs gathered by rank 0
-  __shared__ uint32_t rb[PR];
+  uint32_t* skey = reinterpret_cast<uint32_t*>(sc + PR * NCP);  // [NCP] bit r = pooled row r may see this key
+  __shared__ uint32_t rmask[32];  // per key group: the pooled rows allowed to see it (the pool mask is block-structured:
+  __shared__ uint32_t s_fm;       // a key is visible to ~2 of the 16 rows, so only those dot products are computed)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cl_rank();
   const int cid = blockIdx.x / PC;
@@ -170,17 +172,25 @@ pool_fwd_cl_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict
   const int j0 = static_cast<int>(rank) * NC;
   const int nloc = max(0, min(NC, N - j0));
   for (int i = tid; i < PR * DH; i += 256) q[i] = (i / DH) < R ? qp[(i / DH) * H * DH + h * DH + (i % DH)] : 0.f;
-  if (tid < PR) rb[tid] = tid < R ? rowbits[tid] : 0u;
+  if (tid < 32) {
+    uint32_t m = 0;
+    for (int r = 0; r < R; ++r) m |= ((rowbits[r] >> tid) & 1u) << r;
+    rmask[tid] = m;
+  }
+  if (tid == 0) s_fm = 0u;
   __syncthreads();
-  // ---- phase 1: masked scores of this CTA's keys, thread = key
+  // ---- phase 1: masked scores of this CTA's keys, thread = key; only the rows that may see the key are scored
   for (int jl = tid; jl < nloc; jl += 256) {
     const int j = j0 + jl;
     float k[DH];
     load_row64(kv + (static_cast<long long>(b) * N + j) * ld + h * DH, k);
     const bool pad = padding[static_cast<long long>(b) * N + j] != 0;
-    const uint32_t kg = keygrp[j];
-#pragma unroll 4
-    for (int r = 0; r < PR; ++r) {
+    const uint32_t rs = pad ? 0u : rmask[keygrp[j] & 31u];
+    skey[jl] = rs;
+#pragma unroll
+    for (int r = 0; r < PR; ++r) sc[r * NCP + jl] = -CUDART_INF_F;
+    for (uint32_t m = rs; m != 0u; m &= m - 1u) {
+      const int r = __ffs(m) - 1;
       const float4* q4 = reinterpret_cast<const float4*>(q + r * DH);
       float s = 0.f;
 #pragma unroll
@@ -188,7 +198,7 @@ pool_fwd_cl_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict
         const float4 w = q4[c];
         s += w.x * k[4 * c] + w.y * k[4 * c + 1] + w.z * k[4 * c + 2] + w.w * k[4 * c + 3];
       }
-      sc[r * NCP + jl] = (!pad && ((rb[r] >> kg) & 1u)) ? s : -CUDART_INF_F;
+      sc[r * NCP + jl] = s;
     }
   }
   __syncthreads();
@@ -235,6 +245,7 @@ pool_fwd_cl_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict
       // every key masked: softmax of a constant row = 1/N over all N keys (padded and disallowed ones included)
       const float u = 1.0f / static_cast<float>(N);
       for (int jl = lane; jl < nloc; jl += 32) sc[r * NCP + jl] = u, prow[jl] = u;
+      if (lane == 0) atomicOr(&s_fm, 1u << r);
     } else {
       float tot = 0.f;
 #pragma unroll
@@ -256,6 +267,7 @@ pool_fwd_cl_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict
 #pragma unroll
     for (int r = 0; r < PR; ++r) acc[r] = 0.f;
     const __nv_bfloat16* vcol = kv + (static_cast<long long>(b) * N + j0) * ld + H * DH + h * DH + c;
+    const uint32_t fmm = s_fm;  // fully masked rows weigh every key with 1/N
     for (int jb = g; jb < nloc; jb += 32) {  // eight independent loads in flight per thread
       float v[8];
 #pragma unroll
@@ -263,8 +275,10 @@ pool_fwd_cl_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int jl = jb + 4 * u < nloc ? jb + 4 * u : jb;  // v[u] = 0 beyond the chunk
+        const uint32_t rs = skey[jl] | fmm;                  // warp-uniform (one key per warp and step): rows with p != 0
 #pragma unroll
-        for (int r = 0; r < PR; ++r) acc[r] += sc[r * NCP + jl] * v[u];
+        for (int r = 0; r < PR; ++r)
+          if ((rs >> r) & 1u) acc[r] += sc[r * NCP + jl] * v[u];
       }
     }
 #pragma unroll
@@ -301,6 +315,7 @@ pool_bwd_cl_kernel(const float* __restrict__ dout, const float* __restrict__ qp,
   float* xds = ds + PR * NCP;           // [PC][16] partial row sums of P dP
   float* part = xds + 2 * PC * PR;      // [4][16][64]
   float* xpart = part + 4 * PR * DH;    // [PC][16][64]
+  uint32_t* skey = reinterpret_cast<uint32_t*>(xpart);  // [NCP] bit r = P[r, key] != 0 (xpart is only used at the end)
   __shared__ uint8_t fm[PR];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cl_rank();
@@ -316,13 +331,26 @@ pool_bwd_cl_kernel(const float* __restrict__ dout, const float* __restrict__ qp,
   }
   if (tid < PR) fm[tid] = tid < R ? full_masked[b * R + tid] : 1;
   __syncthreads();
-  // ---- dP[r, j] = g[r] . V[j], thread = key
+  // ---- dP[r, j] = g[r] . V[j], thread = key.  The pool mask is block-structured: a key carries probability in ~2 of
+  // the 16 rows, and only those rows (minus the fully masked ones, whose scores get no gradient) need dP.
   for (int jl = tid; jl < nloc; jl += 256) {
     const int j = j0 + jl;
     float v[DH];
     load_row64(kv + (static_cast<long long>(b) * N + j) * ld + H * DH + h * DH, v);
-#pragma unroll 4
+    uint32_t rs = 0u, live = 0u;
+#pragma unroll
     for (int r = 0; r < PR; ++r) {
+      const float pv = r < R ? probs[(static_cast<long long>(b * H + h) * R + r) * N + j] : 0.f;
+      ps[r * NCP + jl] = pv;
+      ds[r * NCP + jl] = 0.f;
+      if (pv != 0.f) {
+        rs |= 1u << r;
+        if (fm[r] == 0) live |= 1u << r;
+      }
+    }
+    skey[jl] = rs;
+    for (uint32_t m = live; m != 0u; m &= m - 1u) {
+      const int r = __ffs(m) - 1;
       const float4* g4 = reinterpret_cast<const float4*>(g + r * DH);
       float s = 0.f;
 #pragma unroll
@@ -331,7 +359,6 @@ pool_bwd_cl_kernel(const float* __restrict__ dout, const float* __restrict__ qp,
         s += w.x * v[4 * c] + w.y * v[4 * c + 1] + w.z * v[4 * c + 2] + w.w * v[4 * c + 3];
       }
       ds[r * NCP + jl] = s;
-      ps[r * NCP + jl] = r < R ? probs[(static_cast<long long>(b * H + h) * R + r) * N + j] : 0.f;
     }
   }
   __syncthreads();
@@ -364,8 +391,10 @@ pool_bwd_cl_kernel(const float* __restrict__ dout, const float* __restrict__ qp,
         float ak[16], av[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) ak[i] = 0.f, av[i] = 0.f;
+        const uint32_t rs = skey[jl];
 #pragma unroll 2
         for (int r = 0; r < PR; ++r) {
+          if (!((rs >> r) & 1u)) continue;  // P = dS = 0 for this (row, key)
           const float s = ds[r * NCP + jl], p = ps[r * NCP + jl];
           const float4* q4 = reinterpret_cast<const float4*>(q + r * DH + c0);
           const float4* g4 = reinterpret_cast<const float4*>(g + r * DH + c0);
@@ -406,8 +435,10 @@ pool_bwd_cl_kernel(const float* __restrict__ dout, const float* __restrict__ qp,
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int jl = jb + 4 * u < nloc ? jb + 4 * u : jb;  // kx[u] = 0 beyond the chunk
+        const uint32_t rs = skey[jl];                        // warp-uniform
 #pragma unroll
-        for (int r = 0; r < PR; ++r) acc[r] += ds[r * NCP + jl] * kx[u];
+        for (int r = 0; r < PR; ++r)
+          if ((rs >> r) & 1u) acc[r] += ds[r * NCP + jl] * kx[u];
       }
     }
 #pragma unroll

@@ -278,10 +278,17 @@ class Engine:
         if world > 1 and want:
             # rebuild the flat parameter / gradient buffers in symmetric memory (peers pull gradient shards from them and
             # push updated parameter shards into them), then the small exchange buffers
-            self._want_symm = True
-            self._flat_ptrs = None
-            self.ensure_flat()
-            self._setup_p2p()
+            try:
+                self._want_symm = True
+                self._flat_ptrs = None
+                self.ensure_flat()
+                self._setup_p2p()
+            except Exception as exc:  # no P2P mapping between these GPUs / symmetric memory unavailable
+                import warnings
+                warnings.warn(f"peer-memory data parallelism unavailable ({type(exc).__name__}: {exc}); "
+                              "using the NCCL all_gather / reduce_scatter / all_reduce form")
+                self._want_symm, self._p2p, self._flat_ptrs = False, None, None
+                self.ensure_flat()
 
     def _setup_p2p(self):
         """One symmetric allocation per rank: [pooled_all G*B*R*D | dpooled_all G*B*R*D | flags (G uint32, padded to 64
