@@ -179,6 +179,83 @@ def algorithmic_flops(plan, B, H, depth, I):
             "ff2": 2 * M * I * d, "out": 2 * M * d * d}
 
 
+def run_infer(args):
+    """Config 5 (infer_accel_gpu.py:88-111): eval-mode forward of the MMA model incl. its losses, every returned embedding
+    read back to the host; N ranks = N independent replicas on disjoint shards (the script asserts world_size == 1)."""
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    from mca_paper_b200 import config as C, synthetic as S
+    from mca_paper_b200.model import MCA
+
+    name = args.config if args.config != "CMU_config1" else "CMU_config1_z_12i"
+    cfg = C.named_config(name)
+    torch.manual_seed(int(cfg["seed"]))
+    model = MCA(**C.get_model_config(cfg)).to(dev).eval()
+    eng = model.engine
+    eng.ensure_flat()
+    eng.pack_weights()
+    host = S.make_batch(cfg, seed=1 + rank, variant=args.variant)
+    pinned = {m: {k: v.pin_memory() for k, v in d.items()} for m, d in host.items()}
+    devb = {m: {k: torch.empty_like(v, device=dev) for k, v in d.items()} for m, d in host.items()}
+    out_pin = torch.empty(eng.B, eng.R, 512, pin_memory=True)
+
+    def fwd():
+        pooled = eng.trunk_forward(devb)
+        eng.loss_forward(pooled)
+
+    def h2d():
+        for m, d in pinned.items():
+            for k, v in d.items():
+                devb[m][k].copy_(v, non_blocking=True)
+
+    h2d()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        fwd(), fwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g), torch.no_grad():
+        fwd()
+    for _ in range(max(args.warmup, 3)):
+        g.replay()
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    for _ in range(args.steps):
+        g.replay()
+    e[1].record()
+    torch.cuda.synchronize()
+    e[2].record()
+    for _ in range(args.steps):
+        h2d()
+        g.replay()
+        out_pin.copy_(eng.ws["pooled"], non_blocking=True)
+    e[3].record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    if rank == 0:
+        h2d_bytes = sum(v.numel() * v.element_size() for d in host.values() for v in d.values())
+        print(json.dumps({
+            "metric": "embedding inference samples/sec (infer_accel_gpu.py forward incl. losses)", "unit": UNIT, "n_gpus": world,
+            "value": world * eng.B * args.steps / (float(t[0]) * 1e-3), "steps": args.steps, "ms_per_step": float(t[0]) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{name} MMA forward, eval/no_grad, B=8 per replica, variant={args.variant}",
+                       "parallelism": f"{world} independent replicas (no collective)"},
+            "e2e": {"value": world * eng.B * args.steps / (float(t[1]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": out_pin.numel() * 4, "ms_per_step": float(t[1]) / args.steps}}), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,9 +266,13 @@ def main():
     ap.add_argument("--variant", default="full")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="infer = SURVEY.md §8d config 5: eval() forward + losses of infer_accel_gpu.py:97-111, replicas only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "infer":
+        return run_infer(args)
     args.warmup = max(args.warmup, 3)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -523,40 +523,63 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
 }
 
-// delta[b,h,n] = sum_c dO*O ; ucorr[b, h*64+c] += dO[row, h*64+c] / N for rows whose lse is +inf (fully masked)
+// delta[b,h,n] = sum_c dO*O ; ucorr[b, h*64+c] += dO[row, h*64+c] / N for rows whose lse is +inf (fully masked).
+// Block (x, b) walks 64 rows of sample b: the masked rows' dO are summed in registers, then across the 8 warps in shared
+// memory, and only then added to ucorr — one atomic per column and block instead of one per column and row (with 40 %
+// modality dropout a third of all rows are fully masked and the per-row atomics on 4096 addresses dominated the step).
+constexpr int PREP_ROWS = 64;
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ ucorr, int B, int N,
                      int H) {
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= static_cast<long long>(B) * N) return;
-  const int b = static_cast<int>(row / N), n = static_cast<int>(row % N);
+  __shared__ float s_part[8][512];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
   const int HD = H * AB_DH;  // 512: each lane owns 16 consecutive columns, 4 lanes per head
   const int c0 = lane * (HD / 32);
-  const uint4* o4 = reinterpret_cast<const uint4*>(out + row * HD + c0);
-  const uint4* d4 = reinterpret_cast<const uint4*>(dout + row * HD + c0);
-  float dv[16];
-  float acc = 0.f;
+  const int h = c0 / AB_DH;
+  float usum[16];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const uint4 o = o4[i], d = d4[i];
-    const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
+  for (int i = 0; i < 16; ++i) usum[i] = 0.f;
+  bool any = false;
+  const int n_end = min(N, (static_cast<int>(blockIdx.x) + 1) * PREP_ROWS);
+  for (int n = blockIdx.x * PREP_ROWS + warp; n < n_end; n += 8) {
+    const long long row = static_cast<long long>(b) * N + n;
+    const uint4* o4 = reinterpret_cast<const uint4*>(out + row * HD + c0);
+    const uint4* d4 = reinterpret_cast<const uint4*>(dout + row * HD + c0);
+    float dv[16];
+    float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dv[8 * i + 2 * j] = bf16_lo(dw[j]), dv[8 * i + 2 * j + 1] = bf16_hi(dw[j]);
-      acc += bf16_lo(ow[j]) * dv[8 * i + 2 * j] + bf16_hi(ow[j]) * dv[8 * i + 2 * j + 1];
+    for (int i = 0; i < 2; ++i) {
+      const uint4 o = o4[i], d = d4[i];
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dv[8 * i + 2 * j] = bf16_lo(dw[j]), dv[8 * i + 2 * j + 1] = bf16_hi(dw[j]);
+        acc += bf16_lo(ow[j]) * dv[8 * i + 2 * j] + bf16_hi(ow[j]) * dv[8 * i + 2 * j + 1];
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    const long long sidx = (static_cast<long long>(b) * H + h) * N + n;
+    if ((lane & 3) == 0) delta[sidx] = acc;
+    if (lse[sidx] == CUDART_INF_F) {
+      any = true;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) usum[i] += dv[i];
     }
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  const int h = c0 / AB_DH;
-  const long long sidx = (static_cast<long long>(b) * H + h) * N + n;
-  if ((lane & 3) == 0) delta[sidx] = acc;
-  if (lse[sidx] == CUDART_INF_F) {
-    const float inv = 1.0f / static_cast<float>(N);
+  const bool block_any = __syncthreads_or(any);
+  if (!block_any) return;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) atomicAdd(ucorr + static_cast<long long>(b) * HD + c0 + i, dv[i] * inv);
+  for (int i = 0; i < 16; ++i) s_part[warp][c0 + i] = usum[i];
+  __syncthreads();
+  const float inv = 1.0f / static_cast<float>(N);
+  for (int c = threadIdx.x; c < HD; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w][c];
+    if (t != 0.f) atomicAdd(ucorr + static_cast<long long>(b) * HD + c, t * inv);
   }
 }
 
@@ -588,7 +611,7 @@ extern "C" int mca_attn_bwd(const void* qkv, const void* out, const void* dout, 
   }
   if (cudaMemsetAsync(dq_accum, 0, M * HD * sizeof(float), stream) != cudaSuccess) return MCA_ERR_CUDA;
   if (cudaMemsetAsync(ucorr, 0, static_cast<size_t>(B) * HD * sizeof(float), stream) != cudaSuccess) return MCA_ERR_CUDA;
-  attn_bwd_prep_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, stream>>>(
+  attn_bwd_prep_kernel<<<dim3((N + PREP_ROWS - 1) / PREP_ROWS, B), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta, ucorr, B, N, H);
   AttnBwdArgs a{k_tiles_q, qt_list, q_tiles, rowbits, keygrp, tile_grp, padding, kt_class, lse, delta, ucorr,
                 reinterpret_cast<__nv_bfloat16*>(dqkv), N, H, n_kt};

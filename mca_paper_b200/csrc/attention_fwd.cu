@@ -315,20 +315,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a)
   }
 }
 
-// vmean[b, c] = mean over all N rows of V[b, :, c]; only needed when some modality is absent (device flag)
+// vmean[b, c] = mean over all N rows of V[b, :, c]; only needed when some modality is absent (device flag).
+// Block (x, b) sums 64 rows of sample b (thread = two adjacent bf16 columns, coalesced 1 KB per row) and adds its partial
+// to vmean (zeroed by the launcher): 40 x B blocks instead of one long-running block per (sample, 128 columns).
+constexpr int VM_ROWS = 64;
 __global__ void __launch_bounds__(256)
 vmean_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int v_col0, int width, int N, const int* __restrict__ any_absent,
              float* __restrict__ vmean) {
   if (*any_absent == 0) return;
-  __shared__ float part[2][128];
-  const int b = blockIdx.x;
-  const int c = blockIdx.y * 128 + (threadIdx.x & 127), g = threadIdx.x >> 7;
-  float acc = 0.f;
-  if (c < width)
-    for (int n = g; n < N; n += 2) acc += __bfloat162float(qkv[(static_cast<long long>(b) * N + n) * ld + v_col0 + c]);
-  part[g][threadIdx.x & 127] = acc;
-  __syncthreads();
-  if (g == 0 && c < width) vmean[static_cast<long long>(b) * width + c] = (part[0][threadIdx.x] + part[1][threadIdx.x]) / N;
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * VM_ROWS, n1 = min(N, n0 + VM_ROWS);
+  const float inv = 1.0f / static_cast<float>(N);
+  for (int c = 2 * threadIdx.x; c < width; c += 2 * blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+    const __nv_bfloat16* col = qkv + static_cast<long long>(b) * N * ld + v_col0 + c;
+#pragma unroll 8
+    for (int n = n0; n < n1; ++n) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(col + static_cast<long long>(n) * ld);
+      a0 += bf16_lo(w), a1 += bf16_hi(w);
+    }
+    atomicAdd(vmean + static_cast<long long>(b) * width + c, a0 * inv);
+    atomicAdd(vmean + static_cast<long long>(b) * width + c + 1, a1 * inv);
+  }
 }
 
 }  // namespace mca
@@ -353,7 +361,8 @@ extern "C" int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int 
       return MCA_ERR_CUDA;
     attr = true;
   }
-  dim3 gv(B, (H * AT_DH + 127) / 128);
+  if (cudaMemsetAsync(vmean, 0, static_cast<size_t>(B) * H * AT_DH * sizeof(float), stream) != cudaSuccess) return MCA_ERR_CUDA;
+  dim3 gv((N + VM_ROWS - 1) / VM_ROWS, B);
   vmean_kernel<<<gv, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ld, 2 * H * AT_DH, H * AT_DH, N,
                                        any_absent, vmean);
   AttnFwdArgs a{q_tiles, kt_list, k_tiles, rowbits, keygrp, tile_grp, kt_class, kt_live, vmean,
