@@ -159,7 +159,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  // columns: [0,128) S^T (queries 0..127), [128,256) dP^T, [256,320) P^T (32) | dS^T (32) of the half in flight,
+  // columns: [0,128) S^T (queries 0..127), [128,256) dP^T, [256,288) P^T (16) | dS^T (16) of half 0's quarter in flight,
+  //          [288,320) the same for half 1,
   //          [320,384) dV, [384,448) dK, [448,512) dQ
   const uint32_t tP = tmem_base + 256, tdV = tmem_base + 320, tdK = tmem_base + 384, tdQ = tmem_base + 448;
   if (threadIdx.x == 0) TRG(0);
@@ -233,15 +234,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
         __syncwarp();
       };
-      auto issue_y = [&](int t, int hf, bool last_of_tile) {
-        const uint64_t off = static_cast<uint64_t>(((t % AB_QSTAGES) * AB_TILE + hf * 8192) >> 4);
-        const uint32_t acc = (t > 0 || hf > 0) ? 1u : 0u;
+      // dV += P^T dO, dK += dS^T Q for one QUARTER (32 queries) of the tile: every warpgroup owns a private 32-column
+      // P^T | dS^T buffer (tP + 32 * half), so it never waits for the other warpgroup's products, only for its own
+      // previous quarter's (which run under its next quarter's exp / multiply work)
+      auto issue_y = [&](int t, int hf, int qd, bool last_of_tile) {
+        const uint64_t off = static_cast<uint64_t>(((t % AB_QSTAGES) * AB_TILE + hf * 8192 + qd * 4096) >> 4);
+        const uint32_t acc = (t > 0 || hf > 0 || qd > 0) ? 1u : 0u;
+        const uint32_t tp = tP + 32 * hf;
         if (elect_one()) {
-          // contraction over the 64 queries of this half: 4 steps of 16 query rows (2 KB of the MN-major B tile)
+          // contraction over the 32 queries of this quarter: 2 steps of 16 query rows (2 KB of the MN-major B tile)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16_ts(tdV, tP + k * 8, do_mn0 + off + k * 128, id_y, k > 0 ? 1u : acc);
-            umma_bf16_ts(tdK, tP + 32 + k * 8, dq_mn0 + off + k * 128, id_y, k > 0 ? 1u : acc);
+          for (int k = 0; k < 2; ++k) {
+            umma_bf16_ts(tdV, tp + k * 8, do_mn0 + off + k * 128, id_y, k > 0 ? 1u : acc);
+            umma_bf16_ts(tdK, tp + 16 + k * 8, dq_mn0 + off + k * 128, id_y, k > 0 ? 1u : acc);
           }
           umma_commit(&y_done[hf]);
           if (last_of_tile) umma_commit(&qdo_empty[t % AB_QSTAGES]);  // Q / dO of this tile are no longer read
@@ -267,16 +272,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           issue_x(t + 1);
         }
         if (lane == 0) TR(2, t, 1);
-        mbar_wait(&c_done[0], ph);
-        if (lane == 0) TR(2, t, 2);
-        tc_fence_after();
-        issue_y(t, 0, false);
-        if (lane == 0) TR(2, t, 3);
-        if (lane == 0) TR(2, t, 4);
-        mbar_wait(&c_done[1], ph);
+        // quarters in the order the warpgroups produce them: (half 0, q 0), (half 1, q 0), (half 0, q 1), (half 1, q 1);
+        // c_done[h] completes twice per tile: phase parity = quarter index
+#pragma unroll
+        for (int qd = 0; qd < 2; ++qd) {
+          mbar_wait(&c_done[0], static_cast<uint32_t>(qd));
+          tc_fence_after();
+          issue_y(t, 0, qd, false);
+          mbar_wait(&c_done[1], static_cast<uint32_t>(qd));
+          tc_fence_after();
+          issue_y(t, 1, qd, qd == 1);
+        }
         if (lane == 0) TR(2, t, 5);
-        tc_fence_after();
-        issue_y(t, 1, true);
         if (t > 0) {
           mbar_wait(dq_free, (t - 1) & 1);
           tc_fence_after();
@@ -386,6 +393,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       load_q(2);
     }
     mbar_arrive(x_free);  // phase 0: the B rows of tiles 0 and 1 are in place
+    if (kgrp == 255) ab_bar_sync(1 + hf, 128);  // ... and so are their group-bit slots, for every thread of the warpgroup
     for (int t = 0; t < n_iter; ++t) {
       const uint32_t ph = t & 1;
       if (wt == 0) TR(hf, t, 0);
@@ -401,41 +409,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       if (wt == 0) TR(hf, t, 3);
       tc_fence_before();
       mbar_arrive(x_free);  // the next tile's S^T / dP^T may be issued once both warpgroups got here
-      // B rows of tile t + 2 go into the buffer X(t) has just finished with (x_full); X(t + 2) is only issued after
-      // this thread's arrival of iteration t + 1.  Mixed-group key tiles also keep the queries' group bits in shared
-      // memory (by tile % 3): the barrier makes sure nobody still reads the slot being replaced (tile t - 1) and
-      // publishes the bits written in earlier iterations.
-      if (kgrp == 255) ab_bar_sync(1 + hf, 128);
-      write_ext(t + 2);
-      load_q(t + 3);
       if (wt == 0) TR(hf, t, 9);
       const uint32_t* rbq = s_rb[hf][t % 3];
-      // accumulators already hold S^T - lse[q] and dP^T - delta[q]:  P^T = exp2(log2e * .),  dS^T = P^T * (.)
-#pragma unroll
-      for (int e = 0; e < 64; ++e) {
-        const float pi = fast_ex2(__uint_as_float(sv[e >> 5][e & 31]) * AB_LOG2E);
-        sv[e >> 5][e & 31] = __float_as_uint(pi);
-        dv[e >> 5][e & 31] = __float_as_uint(pi * __uint_as_float(dv[e >> 5][e & 31]));
-      }
-      if (kgrp == 255) {  // mixed key groups (fusion sub-blocks): per-(query, key) visibility
-#pragma unroll
-        for (int e = 0; e < 64; ++e)
-          if (!((rbq[e] >> mygrp) & 1u)) sv[e >> 5][e & 31] = 0u, dv[e >> 5][e & 31] = 0u;
-      }
-      if (dead) {
-#pragma unroll
-        for (int e = 0; e < 64; ++e) sv[e >> 5][e & 31] = 0u, dv[e >> 5][e & 31] = 0u;
-      }
-      uint32_t pp[32], dd[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int e = 2 * j;
-        pp[j] = pack_bf16x2(__uint_as_float(sv[e >> 5][e & 31]), __uint_as_float(sv[(e + 1) >> 5][(e + 1) & 31]));
-        dd[j] = pack_bf16x2(__uint_as_float(dv[e >> 5][e & 31]), __uint_as_float(dv[(e + 1) >> 5][(e + 1) & 31]));
-      }
-      if (wt == 0) TR(hf, t, 8);
-      // dS^T -> shared memory for the dQ product.  Half 0 is double buffered by tile parity; half 1 has one buffer
-      // that dQ(t-1) must have finished reading.
+      // dS^T also goes to shared memory for the dQ product.  Half 0 is double buffered by tile parity; half 1 has one
+      // buffer that dQ(t-1) must have finished reading.
       uint8_t* ds_row;
       if (hf == 0) {
         if (t >= 2) mbar_wait(&z_full[t & 1], ((t - 2) >> 1) & 1);
@@ -444,26 +421,58 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         if (t >= 1) mbar_wait(&z_full[(t - 1) & 1], ((t - 1) >> 1) & 1);
         ds_row = sdS + 2 * (AB_DS / 2) + r * 128;
       }
+      const uint32_t tp_mine = tP + 32 * hf + lane_sel;  // this warpgroup's private P^T (16 columns) | dS^T (16 columns)
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(ds_row + ((c ^ (r & 7)) << 4)) = make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
-      // the P^T / dS^T columns are shared by both halves: wait until the previous half's dV / dK products retired
-      if (wt == 0) TR(hf, t, 4);
-      if (hf == 1) {  // half 1 of tile t follows half 0 of tile t; half 0 of tile t follows half 1 of tile t - 1
-        mbar_wait(&y_done[0], ph);
-        tc_fence_after();
-      } else if (t > 0) {
-        mbar_wait(&y_done[1], ph ^ 1);
-        tc_fence_after();
+      for (int qd = 0; qd < 2; ++qd) {  // the half's 64 queries as two quarters of 32: sv[qd], dv[qd]
+        // accumulators already hold S^T - lse[q] and dP^T - delta[q]:  P^T = exp2(log2e * .),  dS^T = P^T * (.)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float pi = fast_ex2(__uint_as_float(sv[qd][e]) * AB_LOG2E);
+          sv[qd][e] = __float_as_uint(pi);
+          dv[qd][e] = __float_as_uint(pi * __uint_as_float(dv[qd][e]));
+        }
+        if (kgrp == 255) {  // mixed key groups (fusion sub-blocks): per-(query, key) visibility
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (!((rbq[qd * 32 + e] >> mygrp) & 1u)) sv[qd][e] = 0u, dv[qd][e] = 0u;
+        }
+        if (dead) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sv[qd][e] = 0u, dv[qd][e] = 0u;
+        }
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          pp[j] = pack_bf16x2(__uint_as_float(sv[qd][2 * j]), __uint_as_float(sv[qd][2 * j + 1]));
+          dd[j] = pack_bf16x2(__uint_as_float(dv[qd][2 * j]), __uint_as_float(dv[qd][2 * j + 1]));
+        }
+        if (wt == 0 && qd == 1) TR(hf, t, 8);
+        // this quarter's 32 queries = bytes [64 qd, 64 qd + 64) of the key's dS row (128B-swizzled 16-byte chunks)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(ds_row + (((4 * qd + c) ^ (r & 7)) << 4)) = make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
+        if (wt == 0 && qd == 1) TR(hf, t, 4);
+        // the private buffer is free once this warpgroup's previous quarter's dV / dK products retired
+        if (t > 0 || qd > 0) {
+          mbar_wait(&y_done[hf], static_cast<uint32_t>(qd ^ 1));  // commit index 2t + qd - 1
+          tc_fence_after();
+        }
+        if (wt == 0 && qd == 1) TR(hf, t, 5);
+        tmem_st16(tp_mine, pp);
+        tmem_st16(tp_mine + 16, dd);
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&c_done[hf]);
       }
-      if (wt == 0) TR(hf, t, 5);
-      tmem_st32(tP + lane_sel, pp);
-      tmem_st32(tP + 32 + lane_sel, dd);
-      tmem_st_wait();
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&c_done[hf]);
       if (wt == 0) TR(hf, t, 6);
+      // B rows of tile t + 2 go into the buffer X(t) has finished with (x_full was observed above); X(t + 2) is only
+      // issued after this thread's x_free arrival of iteration t + 1, so the write is off the critical path.  Mixed-group
+      // key tiles also keep the queries' group bits in shared memory (slot tile % 3): the barrier makes sure nobody still
+      // reads the slot being replaced (tile t - 1) and publishes the slots written in earlier iterations.
+      if (kgrp == 255) ab_bar_sync(1 + hf, 128);
+      write_ext(t + 2);
+      load_q(t + 3);
       // the two warpgroups take turns draining dQ: tile tp is handled by warpgroup tp & 1 one iteration later
       if (t > 0 && ((t - 1) & 1) == hf) drain_dq(t - 1);
       if (wt == 0) TR(hf, t, 7);
