@@ -90,6 +90,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sZ = sBX + 2 * AB_EXT_TILE;        //               the shared all-zero second k chunk
   __shared__ int2 s_qt[AB_MAX_ITERS];                 // (start, len) of every query tile this CTA visits
   __shared__ __align__(16) uint32_t s_rb[2][3][64];   // allowed-key-group bits (mixed-group tiles only), by tile % 3
+  __shared__ float s_uc[AB_DH];  // this (sample, head)'s uniform-row correction of dV, fetched up front
   __shared__ uint64_t bars[24];
   __shared__ uint32_t tmem_holder_s;
   uint64_t* kv_full = bars + 0;
@@ -147,6 +148,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const mca_attn_tile Q = a.q_tiles[a.qt_list[KT.kt_off + i].tile];
     s_qt[i] = make_int2(Q.start, Q.len);
   }
+  if (threadIdx.x >= 256 && threadIdx.x < 256 + AB_DH)
+    s_uc[threadIdx.x - 256] = a.ucorr[static_cast<long long>(b) * HD + h * AB_DH + threadIdx.x - 256];
   // constant rows of the extra k-step (bf16 1.0 = 0x3F80) and the zero block
   for (int i = threadIdx.x; i < 3 * AB_T; i += AB_THREADS) {
     const int row = i & 127, which = i >> 7;
@@ -490,23 +493,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const bool store = r < KT.len;
       const int which = hf;  // 0: dK -> column block 1, 1: dV -> column block 2
       __nv_bfloat16* dst = a.dqkv + (row0 + KT.start + (store ? r : 0)) * (3 * HD) + h * AB_DH + (which + 1) * HD;
-      const float* uc = a.ucorr + static_cast<long long>(b) * HD + h * AB_DH;
+      uint32_t t0[32], t1[32];
+      if (n_iter > 0) {  // both 32-column halves of the accumulator in flight before the wait
+        tmem_ld32((which == 0 ? tdK : tdV) + lane_sel, t0);
+        tmem_ld32((which == 0 ? tdK : tdV) + lane_sel + 32, t1);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t0[i] = 0u, t1[i] = 0u;
+      }
 #pragma unroll
       for (int cc = 0; cc < AB_DH / 32; ++cc) {
         float v[32];
-        if (n_iter > 0) {
-          uint32_t tt[32];
-          tmem_ld32((which == 0 ? tdK : tdV) + lane_sel + cc * 32, tt);
-          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(tt[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cc == 0 ? t0[i] : t1[i]);
         if (which == 1) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += uc[cc * 32 + i];
+          for (int i = 0; i < 32; ++i) v[i] += s_uc[cc * 32 + i];
         }
         if (store) {
 #pragma unroll

@@ -206,6 +206,12 @@ class MCA(nn.Module):
     def forward(self, batch, no_loss=False):
         eng = self._engine
         eng.ensure_flat()
+        # data parallel without the fused Trainer (the reference loop: model(batch); loss.backward() under DDP): the loss
+        # gathers the pooled embeddings across the default process group like gather_tensor does (utils/distributed.py:
+        # 23-56), through NCCL — the peer-memory exchange is set up by Trainer / Engine.set_distributed(p2p=True)
+        if (eng.world == 1 and torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1 and torch.distributed.get_backend() == "nccl"):
+            eng.set_distributed(torch.distributed.get_world_size(), torch.distributed.get_rank(), None, p2p=False)
         eng.pack_weights()
         params = [p for _, p in eng._param_list()]
         want_loss = not no_loss
