@@ -333,9 +333,14 @@ class Engine:
 
     def shard(self):
         """Flat-buffer range [off, off + n) this rank owns in the sharded optimiser step."""
-        per = ((self.n_flat + self.world - 1) // self.world + 3) // 4 * 4
+        per = Engine.shard_size(self.n_flat, self.world)
         off = min(self.rank * per, self.n_flat)
         return off, max(0, min(per, self.n_flat - off))
+
+    @staticmethod
+    def shard_size(n_flat: int, world: int) -> int:
+        """Elements per rank of the sharded optimiser step (float4 units; the last shard may be shorter)."""
+        return ((n_flat + world - 1) // world + 3) // 4 * 4
 
     def check_p2p(self):
         """Raises if a peer missed a flag barrier (read once per run, not per step)."""
@@ -720,6 +725,50 @@ class Engine:
                             schedule="constant", warmup_steps=0, total_steps=1):
         self.adamw_cfg = ops.AdamWCfg(lr, betas[0], betas[1], eps, weight_decay, max_norm,
                                       1 if schedule == "cosine" else 0, warmup_steps, total_steps)
+
+    def optimizer_state_dict(self):
+        """AdamW state in `torch.optim.AdamW.state_dict()` layout ({'state': {i: {step, exp_avg, exp_avg_sq}},
+        'param_groups': [...]}, parameters numbered in `named_parameters()` order) so that a checkpoint written through
+        accelerate's `save_state` (train_accel_gpu.py:122-123,133-134) can be produced / consumed.  Under peer-memory
+        data parallelism every rank only holds the moments of its own shard: they are gathered here (one all-gather of
+        the flat buffers over the process group; checkpoints are rare, the step itself never needs the full moments)."""
+        self.ensure_flat()
+        m, v = self.exp_avg, self.exp_avg_sq
+        if self.world > 1 and self._p2p is not None:
+            off, n = self.shard()
+            per = Engine.shard_size(self.n_flat, self.world)
+            full = []
+            for buf in (m, v):
+                mine = torch.zeros(per, device=self.device, dtype=torch.float32)
+                mine[:n] = buf[off:off + n]
+                out = torch.empty(per * self.world, device=self.device, dtype=torch.float32)
+                torch.distributed.all_gather_into_tensor(out, mine, group=self.group)
+                full.append(out[:self.n_flat])
+            m, v = full
+        step = int(self.step_dev.item())
+        state = {}
+        for i, (name, p) in enumerate(self._param_list()):
+            o = self.offs[name]
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": m[o:o + p.numel()].view(p.shape).clone(),
+                        "exp_avg_sq": v[o:o + p.numel()].view(p.shape).clone()}
+        c = self.adamw_cfg
+        group = {"lr": c.lr, "betas": (c.beta1, c.beta2), "eps": c.eps, "weight_decay": c.weight_decay, "amsgrad": False,
+                 "params": list(range(len(state)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of optimizer_state_dict (also accepts the dict of a torch.optim.AdamW over the same parameters)."""
+        self.ensure_flat()
+        step = 0
+        for i, (name, p) in enumerate(self._param_list()):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            o = self.offs[name]
+            self.exp_avg[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1).to(self.device, torch.float32))
+            self.exp_avg_sq[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1).to(self.device, torch.float32))
+            step = max(step, int(float(st["step"])))
+        self.step_dev.fill_(step)
 
     def optimizer_step(self):
         """Gradient all-reduce (data parallel mean, train_accel_gpu.py:93,115) + clip + AdamW + weight re-pack.

@@ -164,6 +164,13 @@ class Trainer:
                     g()
         return self.eng.ws["summary"]
 
+    def optimizer_state_dict(self):
+        """torch.optim.AdamW-layout optimiser state (gathered across ranks under peer-memory data parallelism)."""
+        return self.eng.optimizer_state_dict()
+
+    def load_optimizer_state_dict(self, sd):
+        self.eng.load_optimizer_state_dict(sd)
+
     def step(self, host_batch):
         """End-to-end step from a HOST batch (dict of dict of CPU tensors): pinned staging, H2D, fused step."""
         self.stage(host_batch)

