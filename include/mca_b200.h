@@ -158,6 +158,19 @@ int mca_patchify(const float* values, int B, int H, int W, int p1, int p2, float
 int mca_dropout_rows(float* x, int B, int L, int d, int rows_per_b, int row_off, float p, unsigned long long seed,
                      const long long* counter_dev, void* stream);
 
+/* Device-side collate, the producer of the hot path's batch (MultimodalCollator encoders.py:374-403 over
+ * EmbeddedSequenceCollator :314-343, SequenceCollator :286-311, MatrixCollator :346-364).  The host stages the live rows
+ * of the present samples back to back (row_off[B+1], absent modality = empty range) and these kernels expand them:
+ * rows: out[b,l,:] = l < len_b ? src[row_off[b]+l,:] : fill (clean != 0: torch.nan_to_num), rows beyond L truncated,
+ *       mask[b,l] = (l >= len_b) as bytes (nullptr: no mask);
+ * values: out[b,l] = l < len_b ? src[off[b]+l] : pad_token, mask[b,l] = (out[b,l] == pad_token) as int64. */
+int mca_collate_rows(const float* src, const int* row_off, int B, int L, int E, float fill, int clean, float* out,
+                     uint8_t* mask, void* stream);
+int mca_collate_values_f32(const float* src, const int* off, int B, int L, float pad_token, float* out, long long* mask,
+                           void* stream);
+int mca_collate_values_i64(const long long* src, const int* off, int B, int L, long long pad_token, long long* out,
+                           long long* mask, void* stream);
+
 /* fusion tokens: broadcast into the packed buffer (model.py:460-461) / batch-sum of their gradient */
 int mca_broadcast_rows(const float* src, float* dst, int F, int d, int B, int rows_per_b, int row_off, void* stream);
 int mca_batchsum_rows(const float* src, float* out, int F, int d, int B, int rows_per_b, int row_off, int accumulate,

@@ -185,9 +185,86 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld
   }
 }
 
+// ------------------------------------------------------------------ device-side collate
+// The step in front of the hot path: MultimodalCollator (encoders.py:286-403).  The host stages only the LIVE rows of
+// the present samples back to back (varlen: nothing is copied for absent modalities or for padding) with B+1 row
+// offsets; these kernels expand them into the collators' dense layouts and build the masks.
+// rows kernel: out[b, l, :] = l < len_b ? clean(src[off_b + l, :]) : fill; mask[b, l] = l >= len_b (truncation to L)
+// one warp per output row (b, l): the row's length test and source offset are computed once, lanes stride over E
+__global__ void __launch_bounds__(256)
+collate_rows_kernel(const float* __restrict__ src, const int* __restrict__ row_off, int B, int L, int E, float fill,
+                    int clean, float* __restrict__ out, uint8_t* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const long long n_rows = static_cast<long long>(B) * L;
+  for (long long t = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); t < n_rows;
+       t += static_cast<long long>(gridDim.x) * 8) {
+    const int l = static_cast<int>(t % L), b = static_cast<int>(t / L);
+    const int o = row_off[b], len = min(row_off[b + 1] - o, L);
+    float* dst = out + t * E;
+    if (l < len) {
+      const float* s = src + (static_cast<long long>(o) + l) * E;
+      for (int e = lane; e < E; e += 32) {
+        float v = s[e];
+        if (clean) {  // torch.nan_to_num defaults: nan -> 0, +-inf -> +-FLT_MAX
+          if (isnan(v)) v = 0.f;
+          else if (isinf(v)) v = v > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+        }
+        dst[e] = v;
+      }
+    } else {
+      for (int e = lane; e < E; e += 32) dst[e] = fill;
+    }
+    if (mask != nullptr && lane == 0) mask[t] = l >= len ? 1 : 0;
+  }
+}
+
+// values kernel (SequenceCollator): out[b, l] = l < len_b ? src[off_b + l] : pad_token; mask[b, l] = (out == pad_token)
+// as int64 — a pad value INSIDE the data is masked too (encoders.py:307)
+template <typename T>
+__global__ void __launch_bounds__(256)
+collate_values_kernel(const T* __restrict__ src, const int* __restrict__ off, int B, int L, T pad_token,
+                      T* __restrict__ out, long long* __restrict__ mask) {
+  const long long n = static_cast<long long>(B) * L;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int l = static_cast<int>(i % L), b = static_cast<int>(i / L);
+    const int o = off[b], len = off[b + 1] - o;
+    const T v = l < len ? src[o + l] : pad_token;
+    out[i] = v;
+    if (mask != nullptr) mask[i] = v == pad_token ? 1 : 0;
+  }
+}
+
 }  // namespace mca
 
 using namespace mca;
+
+extern "C" int mca_collate_rows(const float* src, const int* row_off, int B, int L, int E, float fill, int clean, float* out,
+                                uint8_t* mask, void* stream) {
+  if (B <= 0 || L <= 0 || E <= 0) return MCA_ERR_SHAPE;
+  const long long n_rows = static_cast<long long>(B) * L;
+  const unsigned grid = static_cast<unsigned>((n_rows + 7) / 8 < 148 * 16 ? (n_rows + 7) / 8 : 148 * 16);
+  collate_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, row_off, B, L, E, fill, clean, out, mask);
+  return check_launch();
+}
+
+extern "C" int mca_collate_values_f32(const float* src, const int* off, int B, int L, float pad_token, float* out,
+                                      long long* mask, void* stream) {
+  if (B <= 0 || L <= 0) return MCA_ERR_SHAPE;
+  const long long n = static_cast<long long>(B) * L;
+  collate_values_kernel<float><<<static_cast<unsigned>((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, off, B, L, pad_token, out, mask);
+  return check_launch();
+}
+
+extern "C" int mca_collate_values_i64(const long long* src, const int* off, int B, int L, long long pad_token,
+                                      long long* out, long long* mask, void* stream) {
+  if (B <= 0 || L <= 0) return MCA_ERR_SHAPE;
+  const long long n = static_cast<long long>(B) * L;
+  collate_values_kernel<long long><<<static_cast<unsigned>((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, off, B, L, pad_token, out, mask);
+  return check_launch();
+}
 
 extern "C" int mca_build_offsets(const void* const* masks_host, const int* elem_sizes_host, const int* lens_host,
                                  int n_mod, int B, int N, const int* kt_start, const int* kt_len, int n_kt,

@@ -59,6 +59,9 @@ _SIGS = {
     "mca_embedding_scatter_add": [VP, VP, I32, I32, I32, I32, I32, I32, I32, VP, VP],
     "mca_patchify": [VP, I32, I32, I32, I32, I32, F32, VP, VP, VP],
     "mca_dropout_rows": [VP, I32, I32, I32, I32, I32, F32, C.c_uint64, VP, VP],
+    "mca_collate_rows": [VP, VP, I32, I32, I32, F32, I32, VP, VP, VP],
+    "mca_collate_values_f32": [VP, VP, I32, I32, F32, VP, VP, VP],
+    "mca_collate_values_i64": [VP, VP, I32, I32, I64, VP, VP, VP],
     "mca_tabular_fwd": [VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_tabular_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_embedding_renorm": [VP, I32, I32, F32, VP],

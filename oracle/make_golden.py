@@ -126,6 +126,67 @@ def make_static():
         print(k, v["n_params"], v["attn_allowed_pairs"], len(v["loss_names"]))
 
 
+COLLATE_CONFIG = {
+    "speech": {"type": "embedded_sequence", "pad_len": 12, "data_col_name": "data", "pad_token": -10000, "embedding_size": 5,
+               "dropout": 0.3},
+    "expr": {"type": "sequence", "pad_len": 9, "data_col_name": "values", "pad_token": -10000, "dropout": 0.3},
+    "text": {"type": "sequence", "pad_len": 7, "data_col_name": "indices", "pad_token": 0},
+    "spec": {"type": "matrix", "pad_len": 6, "pad_token": -10000, "max_channels": 4},
+}
+
+
+def collate_samples(seed: int, batch_size: int = 8):
+    """Ragged synthetic samples in the reference's per-sample layout: absent modalities (None), over-long sequences
+    (truncation), NaN / inf entries (clean), pad values inside the data (TCGA protein convention)."""
+    g = torch.Generator().manual_seed(seed)
+    samples = []
+    for b in range(batch_size):
+        n = int(torch.randint(0, 17, (1,), generator=g))
+        sp = torch.randn(n, 5, generator=g)
+        if n > 2:
+            sp[1, 2], sp[2, 0], sp[0, 4] = float("nan"), float("inf"), float("-inf")
+        ex = torch.randn(int(torch.randint(1, 10, (1,), generator=g)), generator=g)
+        if ex.numel() > 3:
+            ex[2] = -10000.0
+        tx = torch.randint(1, 50, (int(torch.randint(1, 8, (1,), generator=g)),), generator=g)
+        mt = torch.randn(int(torch.randint(1, 7, (1,), generator=g)), 4, generator=g)
+        samples.append({
+            "speech": {"data": None if b == 3 else sp},
+            "expr": {"values": None if b == 5 else ex},
+            "text": {"indices": tx, "data": torch.randn(tx.numel(), generator=g)},
+            "spec": {"values": None if b == 6 else mt},
+        })
+    return samples
+
+
+def make_collate_golden():
+    """Outputs of the LIVE reference collators (encoders.py:374-403) and of its dataset-time modality dropout
+    (utils/dataset.py:29-57) on collate_samples(seed)."""
+    ref_shim.load_reference()
+    import encoders as ref_enc  # the reference's module (sys.path set up by ref_shim)
+    from utils import dataset as ref_ds
+    gold = {}
+    for seed in (11, 12):
+        samples = collate_samples(seed)
+        out = ref_enc.MultimodalCollator(COLLATE_CONFIG)([{k: dict(v) for k, v in s.items()} for s in samples])
+        gold[f"collate_{seed}"] = {k: {kk: vv.clone() for kk, vv in v.items()} for k, v in out.items()}
+        # dropout decisions of BatchPreDropout, one instance per modality as batch_predrop builds them
+        torch.manual_seed(100 + seed)
+        drops = {k: ref_ds.BatchPreDropout(kvs={"attention_mask": c["pad_token"], "data": 0.0}, dropout=c["dropout"])
+                 for k, c in COLLATE_CONFIG.items() if c.get("dropout")}
+        dropped = []
+        for s in samples:
+            row = {}
+            for k, v in s.items():
+                if k in drops:
+                    res = drops[k]({kk: vv for kk, vv in v.items()})
+                    row[k] = all(x is None for x in res.values())
+            dropped.append(row)
+        gold[f"dropped_{seed}"] = dropped
+    torch.save(gold, os.path.join(GOLDEN_DIR, "collate.pt"))
+    print("collate golden:", {k: (list(v.keys()) if isinstance(v, dict) else len(v)) for k, v in gold.items()})
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit("the live reference is not present; golden fixtures can only be regenerated in the build container")
@@ -133,6 +194,7 @@ def main():
     for name, spec in CASES.items():
         make_case(name, spec)
     make_static()
+    make_collate_golden()
 
 
 if __name__ == "__main__":
