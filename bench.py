@@ -462,6 +462,7 @@ def main():
             "per_kernel_ms_per_step": {k: round(v["ms_total_per_step"], 4) for k, v in list(per_kernel.items())[:12]} if per_kernel else None,
         }
         print(json.dumps(line), flush=True)
+    eng.check_p2p()  # raises if a peer GPU missed one of the flag barriers (would invalidate the number)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -72,6 +72,9 @@ typedef struct {
   float lr, beta1, beta2, eps, weight_decay, max_norm; /* max_norm <= 0: no clipping */
   int lr_mode;                                         /* 0 constant, 1 cosine with linear warm-up */
   long long warmup_steps, total_steps;
+  long long sched_stride;                              /* scheduler.step() calls per optimiser step: accelerate's
+                                                          prepared scheduler advances num_processes times per step
+                                                          (train_accel_gpu.py:93,119); 0 or 1 = once */
 } mca_adamw_cfg;
 
 int mca_version(void);

@@ -39,7 +39,7 @@ sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out)
 __device__ __forceinline__ float scheduled_lr(const mca_adamw_cfg& c, long long step /*1-based*/) {
   if (c.lr_mode == 0) return c.lr;
   // transformers.get_cosine_schedule_with_warmup evaluated at (step-1): scheduler.step() follows optimizer.step()
-  const double cur = static_cast<double>(step - 1);
+  const double cur = static_cast<double>(step - 1) * static_cast<double>(c.sched_stride > 1 ? c.sched_stride : 1);
   if (cur < c.warmup_steps) return c.lr * static_cast<float>(cur / fmax(1.0, static_cast<double>(c.warmup_steps)));
   const double prog = (cur - c.warmup_steps) / fmax(1.0, static_cast<double>(c.total_steps - c.warmup_steps));
   return c.lr * static_cast<float>(fmax(0.0, 0.5 * (1.0 + cos(3.14159265358979323846 * prog))));

@@ -722,9 +722,26 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ optimiser
     def configure_optimizer(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=2.0,
-                            schedule="constant", warmup_steps=0, total_steps=1):
+                            schedule="constant", warmup_steps=0, total_steps=1, scheduler_stride=1):
+        """scheduler_stride: scheduler.step() calls per optimiser step.  The reference prepares its scheduler with
+        accelerate (train_accel_gpu.py:93), whose wrapper advances it num_processes times per step, so a run on G GPUs
+        walks the cosine G times faster than its step count; pass G to reproduce that (Trainer does)."""
         self.adamw_cfg = ops.AdamWCfg(lr, betas[0], betas[1], eps, weight_decay, max_norm,
-                                      1 if schedule == "cosine" else 0, warmup_steps, total_steps)
+                                      1 if schedule == "cosine" else 0, warmup_steps, total_steps,
+                                      max(1, int(scheduler_stride)))
+
+    def lr_at(self, step: int) -> float:
+        """Host mirror of the device schedule (optim.cu scheduled_lr): the learning rate the `step`-th optimiser step
+        (1-based) uses == transformers.get_cosine_schedule_with_warmup after (step-1)*stride scheduler steps."""
+        import math
+        c = self.adamw_cfg
+        if c.lr_mode == 0:
+            return float(c.lr)
+        cur = float(step - 1) * max(1, c.sched_stride)
+        if cur < c.warmup_steps:
+            return float(c.lr) * cur / max(1.0, float(c.warmup_steps))
+        prog = (cur - c.warmup_steps) / max(1.0, float(c.total_steps - c.warmup_steps))
+        return float(c.lr) * max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 
     def optimizer_state_dict(self):
         """AdamW state in `torch.optim.AdamW.state_dict()` layout ({'state': {i: {step, exp_avg, exp_avg_sq}},

@@ -22,7 +22,7 @@ PACK_DESC_DTYPE = np.dtype([
 
 class AdamWCfg(C.Structure):
     _fields_ = [("lr", F32), ("beta1", F32), ("beta2", F32), ("eps", F32), ("weight_decay", F32), ("max_norm", F32),
-                ("lr_mode", I32), ("warmup_steps", I64), ("total_steps", I64)]
+                ("lr_mode", I32), ("warmup_steps", I64), ("total_steps", I64), ("sched_stride", I64)]
 
 
 _SIGS = {

@@ -23,13 +23,17 @@ from .engine import Engine
 class Trainer:
     def __init__(self, model, lr: float = 1e-4, clip: float = 2.0, weight_decay: float = 0.01, betas=(0.9, 0.999),
                  eps: float = 1e-8, schedule: str = "constant", warmup_steps: int = 0, total_steps: int = 1,
-                 use_graphs: bool = True, process_group=None):
+                 use_graphs: bool = True, process_group=None, scheduler_stride: Optional[int] = None):
         self.model = model
         self.eng: Engine = model.engine
         self.eng.ensure_flat()
+        dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        if scheduler_stride is None:  # accelerate's scheduler wrapper steps once per process (train_accel_gpu.py:93,119)
+            scheduler_stride = torch.distributed.get_world_size(process_group) if dist else 1
         self.eng.configure_optimizer(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=clip,
-                                     schedule=schedule, warmup_steps=warmup_steps, total_steps=total_steps)
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+                                     schedule=schedule, warmup_steps=warmup_steps, total_steps=total_steps,
+                                     scheduler_stride=scheduler_stride)
+        if dist:
             self.eng.set_distributed(torch.distributed.get_world_size(process_group),
                                      torch.distributed.get_rank(process_group), process_group)
         self.use_graphs = use_graphs
