@@ -261,6 +261,27 @@ int mca_dp_adamw_shard(float* const* params_peers_dev, int world, int rank, cons
                        long long* step_dev, float* total_norm_out, float grad_scale, const mca_adamw_cfg* cfg_host,
                        void* stream);
 
+/* ---- Embedding-space evaluation metrics (utils/metrics.py; eval loop train_accel_gpu.py:136-184, infer_accel_gpu.py:115-147,
+ * lp_accel_gpu.py:70-95).  All inputs fp32 row-major [rows, D] on the device; `scratch` holds at least
+ * mca_metric_scratch_doubles(M) doubles; results are single floats / int64 ranks on the device (no host sync). */
+long long mca_metric_scratch_doubles(long long M);
+/* inv[i] = 1 / max(||x_i||_2, eps)  (F.normalize: eps 1e-12, utils/metrics.py:21-22,27; nn.CosineSimilarity: eps 1e-8, :75-76) */
+int mca_row_inv_norms(const float* x, long long M, int D, float eps, float* inv, void* stream);
+/* lalign, utils/metrics.py:20-23: out = mean_i ||x_i - y_i||_2 ^ alpha, rows L2-normalised first when norm != 0
+ * (M == 0 -> NaN like the mean of an empty tensor). */
+int mca_alignment(const float* x, const float* y, long long M, int D, float alpha, int norm, double* scratch, float* out,
+                  void* stream);
+/* lunif, utils/metrics.py:26-29: out = log(mean_{i<j} exp(-t * ||x_i - x_j||^2))  (torch.pdist pairs; M < 2 -> NaN).
+ * inv_scratch: M floats. */
+int mca_uniformity(const float* x, long long M, int D, float t, int norm, float* inv_scratch, double* scratch, float* out,
+                   void* stream);
+/* get_rank_metrics / get_rank, utils/metrics.py:73-92: ranks[i] = #{ j : cos(emb_i, targets_j) > cos(emb_i, targets_idx[i]) }
+ * with idx[i] the sample's own row in `targets` (the reference passes the sample's index in the unmasked array).
+ * inv_e [M], inv_t [T], own [M] are float scratch; idx outside [0, T) is the caller's error (the reference raises
+ * IndexError; the host wrapper checks). */
+int mca_retrieval_ranks(const float* emb, const float* targets, const long long* idx, long long M, long long T, int D,
+                        float* inv_e, float* inv_t, float* own, long long* ranks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

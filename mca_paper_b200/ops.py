@@ -59,6 +59,10 @@ _SIGS = {
     "mca_embedding_scatter_add": [VP, VP, I32, I32, I32, I32, I32, I32, I32, VP, VP],
     "mca_patchify": [VP, I32, I32, I32, I32, I32, F32, VP, VP, VP],
     "mca_dropout_rows": [VP, I32, I32, I32, I32, I32, F32, C.c_uint64, VP, VP],
+    "mca_row_inv_norms": [VP, I64, I32, F32, VP, VP],
+    "mca_alignment": [VP, VP, I64, I32, F32, I32, VP, VP, VP],
+    "mca_uniformity": [VP, I64, I32, F32, I32, VP, VP, VP, VP],
+    "mca_retrieval_ranks": [VP, VP, VP, I64, I64, I32, VP, VP, VP, VP, VP],
     "mca_collate_rows": [VP, VP, I32, I32, I32, F32, I32, VP, VP, VP],
     "mca_collate_values_f32": [VP, VP, I32, I32, F32, VP, VP, VP],
     "mca_collate_values_i64": [VP, VP, I32, I32, I64, VP, VP, VP],
@@ -95,7 +99,7 @@ def S():
 # kernels launched by each entry point (memsets not counted) — bench.py reports the per-step total
 KERNELS_PER_CALL = {"mca_build_offsets": 2, "mca_attn_fwd": 2, "mca_attn_bwd": 3, "mca_pool_attn_bwd": 2,
                     "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3, "mca_dp_adamw_shard": 2,
-                    "mca_embedding_renorm_indexed": 2}
+                    "mca_embedding_renorm_indexed": 2, "mca_alignment": 2, "mca_uniformity": 3, "mca_retrieval_ranks": 4}
 COUNT = {"n": 0}
 PROFILE = {"on": False, "events": []}
 RECORD = {"on": False, "calls": []}  # (name, tag, args) of every entry-point call, for isolated device timing

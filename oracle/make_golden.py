@@ -187,14 +187,65 @@ def make_collate_golden():
     print("collate golden:", {k: (list(v.keys()) if isinstance(v, dict) else len(v)) for k, v in gold.items()})
 
 
+def metrics_inputs(seed: int = 11):
+    """Embeddings shaped like the eval loop's (pooled [M, 512] rows): two correlated sets (positive pairs), a mask with
+    holes, and a nearly collapsed set (uniformity close to 0, all cancellation)."""
+    g = torch.Generator().manual_seed(seed)
+    M, D = 150, 512
+    x = torch.randn(M, D, generator=g)
+    y = x + 0.5 * torch.randn(M, D, generator=g)
+    mask = torch.rand(M, generator=g) > 0.3
+    collapsed = torch.randn(1, D, generator=g) + 1e-2 * torch.randn(70, D, generator=g)
+    small = torch.randn(5, 48, generator=g)
+    yr = 0.07 * x + torch.randn(M, D, generator=g)   # weakly aligned targets: retrieval ranks spread over 0..M
+    return {"x": x, "y": y, "yr": yr, "mask": mask, "collapsed": collapsed, "small": small}
+
+
+def make_metrics_golden():
+    """Outputs of the LIVE reference functions utils/metrics.py:20-33,73-99 on metrics_inputs()."""
+    R = ref_shim.load_reference_metrics()
+    inp = metrics_inputs()
+    x, y, mask = inp["x"], inp["y"], inp["mask"]
+    out = {}
+    for norm in (True, False):
+        for alpha in (2, 1, 3.5):
+            out[f"lalign_a{alpha}_n{int(norm)}"] = R.lalign(x, y, alpha, norm)
+        for t in (2, 0.5):
+            out[f"lunif_t{t}_n{int(norm)}"] = R.lunif(x, t, norm)
+            out[f"lunif_collapsed_t{t}_n{int(norm)}"] = R.lunif(inp["collapsed"], t, norm)
+            out[f"lunif_small_t{t}_n{int(norm)}"] = R.lunif(inp["small"], t, norm)
+    out["wang"] = R.wang_loss(x, y)
+    # accumulators: three updates, compute over the concatenation
+    al, un = R.Alignment(), R.Uniformity()
+    for a, b in zip(x.chunk(3), y.chunk(3)):
+        al.update(a, b)
+        un.update(a)
+    out["Alignment"], out["Uniformity"] = al.compute(), un.compute()
+    out["Alignment_norm"], out["Uniformity_norm"] = al.compute(norm=True), un.compute(norm=True)
+    for name, tg in (("easy", y), ("hard", inp["yr"])):
+        med, r1, r5, r10 = R.get_rank_metrics(x, mask, tg, device="cpu")
+        out[f"rank_metrics_{name}"] = torch.stack([med.double(), r1.double(), r5.double(), r10.double()])
+        c = torch.stack([R.compute_cosines(x[i], tg) for i in range(x.shape[0]) if mask[i]])
+        out[f"ranks_{name}"] = R.get_rank(c, torch.nonzero(mask).reshape(-1))
+    gold = {"inputs": inp, "outputs": {k: v.detach().clone() for k, v in out.items()}}
+    torch.save(gold, os.path.join(GOLDEN_DIR, "metrics.pt"))
+    print("metrics golden:", {k: (v.tolist() if v.numel() < 5 else tuple(v.shape)) for k, v in gold["outputs"].items()})
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit("the live reference is not present; golden fixtures can only be regenerated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for name, spec in CASES.items():
-        make_case(name, spec)
-    make_static()
-    make_collate_golden()
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only in ("", "cases"):
+        for name, spec in CASES.items():
+            make_case(name, spec)
+    if only in ("", "static"):
+        make_static()
+    if only in ("", "collate"):
+        make_collate_golden()
+    if only in ("", "metrics"):
+        make_metrics_golden()
 
 
 if __name__ == "__main__":

@@ -88,3 +88,44 @@ def build_reference_model(model_kwargs: dict, state_dict=None):
 def reference_forward(model, batch, no_loss=False):
     with no_debug_save(), contextlib.redirect_stdout(open(os.devnull, "w")):
         return model(batch, no_loss=no_loss)
+
+
+_ref_metrics_module = None
+
+
+def load_reference_metrics():
+    """Import the reference's utils/metrics.py in place (cached).  It subclasses torchmetrics.Metric, which is not
+    installed: a stub `Metric` providing add_state (list states) and `dim_zero_cat` = torch.cat is registered so the
+    module imports; lalign / lunif / get_rank_metrics themselves are plain torch."""
+    global _ref_metrics_module
+    if _ref_metrics_module is not None:
+        return _ref_metrics_module
+    path = os.path.join(REFERENCE_ROOT, "utils", "metrics.py")
+    if not os.path.isfile(path):
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    if "torchmetrics" not in sys.modules:
+        tm, tmu, tmd = (types.ModuleType(n) for n in ("torchmetrics", "torchmetrics.utilities", "torchmetrics.utilities.data"))
+
+        class Metric:
+            def __init__(self, **kwargs):
+                self._defaults = {}
+
+            def add_state(self, name, default, dist_reduce_fx=None):
+                self._defaults[name] = default
+                setattr(self, name, list(default) if isinstance(default, list) else default)
+
+            def reset(self):
+                for k, v in self._defaults.items():
+                    setattr(self, k, list(v) if isinstance(v, list) else v)
+
+        tm.Metric = Metric
+        tmd.dim_zero_cat = lambda x: torch.cat(list(x), 0) if isinstance(x, (list, tuple)) else x
+        tm.utilities, tmu.data = tmu, tmd
+        sys.modules.update({"torchmetrics": tm, "torchmetrics.utilities": tmu, "torchmetrics.utilities.data": tmd})
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_mca_reference_metrics", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _ref_metrics_module = mod
+    return mod

@@ -172,7 +172,7 @@ def test_device_schedule_matches_transformers_cosine():
              torch.cuda.current_stream().cuda_stream)
         used = (1.0 - p[0].item() / before) / wd
         want = opt.param_groups[0]["lr"]
-        assert abs(used - want) <= 2e-6 * lr + 2e-7, (it, used, want)
+        assert abs(used - want) <= 5e-7, (it, used, want)      # fp32 rounding of p bounds the read-back at ~1e-7
         opt.step()
         for _ in range(stride):
             sch.step()
