@@ -59,7 +59,7 @@ alignment_kernel(const float* __restrict__ x, const float* __restrict__ y, long 
     }
     float ss = 0.f;
     for (int c = lane; c < D; c += 32) {
-      const float d = px[c] * sx - py[c] * sy;
+      const float d = __fmul_rn(px[c], sx) - __fmul_rn(py[c], sy);  // normalise, then subtract (no fma contraction)
       ss += d * d;
     }
 #pragma unroll

@@ -34,8 +34,8 @@ def lalign(x, y, alpha=2, norm=True):
     if x.shape != y.shape:
         raise ValueError("preds and target must have the same shape")
     out = torch.empty(1, device=x.device, dtype=torch.float32)
-    call("mca_alignment", P(x), P(y), x.shape[0], x.shape[1], float(alpha), int(bool(norm)), P(_scratch(x.shape[0], x.device)),
-         P(out), S())
+    scratch = _scratch(x.shape[0], x.device)
+    call("mca_alignment", P(x), P(y), x.shape[0], x.shape[1], float(alpha), int(bool(norm)), P(scratch), P(out), S())
     return out[0]
 
 
@@ -45,7 +45,8 @@ def lunif(x, t=2, norm=True):
     M = x.shape[0]
     out = torch.empty(1, device=x.device, dtype=torch.float32)
     inv = torch.empty(max(M, 1), device=x.device, dtype=torch.float32)
-    call("mca_uniformity", P(x), M, x.shape[1], float(t), int(bool(norm)), P(inv), P(_scratch(M, x.device)), P(out), S())
+    scratch = _scratch(M, x.device)
+    call("mca_uniformity", P(x), M, x.shape[1], float(t), int(bool(norm)), P(inv), P(scratch), P(out), S())
     return out[0]
 
 
@@ -131,8 +132,8 @@ def retrieval_ranks(embeddings, targets, indices):
     ranks = torch.zeros(M, device=e.device, dtype=torch.int64)
     if M == 0:
         return ranks
-    f = lambda n: torch.empty(n, device=e.device, dtype=torch.float32)
-    call("mca_retrieval_ranks", P(e), P(t), P(idx), M, T, e.shape[1], P(f(M)), P(f(T)), P(f(M)), P(ranks), S())
+    inv_e, inv_t, own = (torch.empty(n, device=e.device, dtype=torch.float32) for n in (M, T, M))  # distinct live buffers
+    call("mca_retrieval_ranks", P(e), P(t), P(idx), M, T, e.shape[1], P(inv_e), P(inv_t), P(own), P(ranks), S())
     return ranks
 
 
