@@ -2,7 +2,7 @@
 // reference computes them (utils/metrics.py:20-29: F.normalize, (x - y).norm(dim=1).pow(alpha).mean(),
 // torch.pdist(x).pow(2).mul(-t).exp().mean().log()) and the retrieval ranks of utils/metrics.py:73-99 (cosine of every
 // masked embedding against all targets, rank = number of targets scoring above the sample's own).  The O(M^2 D) pair
-// work runs as 64x64 fp32 pair tiles on the CUDA cores (eval-only, exact fp32 differences rather than a Gram-matrix
+// work runs as 128x128 fp32 pair tiles on the CUDA cores (eval-only, exact fp32 differences rather than a Gram-matrix
 // trick: uniformity of nearly collapsed embeddings is all cancellation); sums are reduced through per-block partials
 // in a fixed order, so results are bit-reproducible.
 #include "mca_b200.h"
@@ -11,7 +11,7 @@
 
 namespace mca {
 
-constexpr int MT_TILE = 64, MT_K = 32, MT_STRIDE = 65;
+constexpr int MT_TILE = 128, MT_K = 16, MT_STRIDE = 132;
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -117,17 +117,18 @@ own_cosine_kernel(const float* __restrict__ emb, const float* __restrict__ inv_e
   if (lane == 0) own[r] = s;
 }
 
-// One 64 x 64 tile of (row of A, row of B) pairs per block, rows pre-scaled by inv while staged; 256 threads, 4 x 4
-// pairs each, D walked in chunks of 32 through shared memory.
+// One 128 x 128 tile of (row of A, row of B) pairs per block, rows pre-scaled by inv while staged; 256 threads, 8 x 8
+// pairs each (two 4-row groups x two 4-column groups, so every shared-memory read is a 128-bit load), D walked in chunks
+// of 16 through shared memory with the next chunk's global loads in flight during the FMAs.
 //   MODE 0 (uniformity): A == B; partial[block] = sum over pairs i < j of exp(-t * ||a_i - a_j||^2); tiles below the
 //                        diagonal exit at once.
 //   MODE 1 (ranks):      ranks[i] += #{ j != idx[i] : <a_i, b_j> > own[i] }
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 pair_tile_kernel(const float* __restrict__ A, const float* __restrict__ invA, long long MA, const float* __restrict__ Bm,
                  const float* __restrict__ invB, long long MB, int D, float t, double* __restrict__ partial,
                  const float* __restrict__ own, const long long* __restrict__ idx, unsigned long long* __restrict__ ranks) {
-  __shared__ float As[MT_K][MT_STRIDE], Bs[MT_K][MT_STRIDE];
+  __shared__ __align__(16) float As[MT_K][MT_STRIDE], Bs[MT_K][MT_STRIDE];
   __shared__ double s_w[8];
   const int ti = blockIdx.y, tj = blockIdx.x;
   if (MODE == 0 && tj < ti) {
@@ -136,32 +137,45 @@ pair_tile_kernel(const float* __restrict__ A, const float* __restrict__ invA, lo
   }
   const long long i0 = static_cast<long long>(ti) * MT_TILE, j0 = static_cast<long long>(tj) * MT_TILE;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int lk = threadIdx.x & 31, lr = threadIdx.x >> 5;
-  float acc[4][4];
+  const int lk = threadIdx.x & 15, lr = threadIdx.x >> 4;   // staging: column lk of rows lr, lr + 16, ...
+  float acc[8][8];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
 
-  for (int k0 = 0; k0 < D; k0 += MT_K) {
+  float pa[8], pb[8];   // the staged chunk (scaled by the row's inv, an L1 hit after the first chunk)
+  auto load_chunk = [&](int k0) {
     const int k = k0 + lk;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int row = lr + 8 * e;
-      const long long ia = i0 + row, ib = j0 + row;
-      As[lk][row] = (ia < MA && k < D) ? A[ia * D + k] * invA[ia] : 0.f;
-      Bs[lk][row] = (ib < MB && k < D) ? Bm[ib * D + k] * invB[ib] : 0.f;
+      const long long ia = i0 + lr + 16 * e, ib = j0 + lr + 16 * e;
+      pa[e] = (ia < MA && k < D) ? __fmul_rn(A[ia * D + k], invA[ia]) : 0.f;
+      pb[e] = (ib < MB && k < D) ? __fmul_rn(Bm[ib * D + k], invB[ib]) : 0.f;
     }
-    __syncthreads();
-#pragma unroll 8
+  };
+  auto store_chunk = [&]() {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) As[lk][lr + 16 * e] = pa[e], Bs[lk][lr + 16 * e] = pb[e];
+  };
+  load_chunk(0);
+  store_chunk();
+  __syncthreads();
+  for (int k0 = 0; k0 < D; k0 += MT_K) {
+    const bool more = k0 + MT_K < D;
+    if (more) load_chunk(k0 + MT_K);
+#pragma unroll
     for (int kk = 0; kk < MT_K; ++kk) {
-      float a[4], b[4];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = As[kk][ty * 4 + r], b[r] = Bs[kk][tx * 4 + r];
+      for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 8; ++c) {
           if (MODE == 0) {
             const float d = a[r] - b[c];
             acc[r][c] = fmaf(d, d, acc[r][c]);
@@ -171,15 +185,20 @@ pair_tile_kernel(const float* __restrict__ A, const float* __restrict__ invA, lo
         }
     }
     __syncthreads();
+    if (more) {
+      store_chunk();
+      __syncthreads();
+    }
   }
 
+  // pair (r, c) of this thread = rows i0 + (r < 4 ? 0 : 64) + ty*4 + (r & 3), columns j0 + (c < 4 ? 0 : 64) + tx*4 + (c & 3)
   if (MODE == 0) {
     double s = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const long long i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
+      for (int c = 0; c < 8; ++c) {
+        const long long i = i0 + (r >> 2) * 64 + ty * 4 + (r & 3), j = j0 + (c >> 2) * 64 + tx * 4 + (c & 3);
         if (i < j && j < MA) s += static_cast<double>(expf(-t * acc[r][c]));
       }
     s = warp_sum_f64(s);
@@ -193,15 +212,15 @@ pair_tile_kernel(const float* __restrict__ A, const float* __restrict__ invA, lo
     }
   } else {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const long long i = i0 + ty * 4 + r;
+    for (int r = 0; r < 8; ++r) {
+      const long long i = i0 + (r >> 2) * 64 + ty * 4 + (r & 3);
       int cnt = 0;
       if (i < MA) {
         const float o = own[i];
         const long long self = idx[i];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const long long j = j0 + tx * 4 + c;
+        for (int c = 0; c < 8; ++c) {
+          const long long j = j0 + (c >> 2) * 64 + tx * 4 + (c & 3);
           cnt += (j < MB && j != self && acc[r][c] > o) ? 1 : 0;
         }
       }
