@@ -743,6 +743,18 @@ class Engine:
         prog = (cur - c.warmup_steps) / max(1.0, float(c.total_steps - c.warmup_steps))
         return float(c.lr) * max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 
+    def snapshot_state(self):
+        """Device copies of everything an optimiser step mutates (weights, moments, step, dropout counter)."""
+        snap = {k: getattr(self, k).clone() for k in ("flat", "exp_avg", "exp_avg_sq", "step_dev")}
+        snap["drop_ctr"] = self.ws["drop_ctr"].clone()
+        return snap
+
+    def restore_state(self, snap):
+        for k in ("flat", "exp_avg", "exp_avg_sq", "step_dev"):
+            getattr(self, k).copy_(snap[k])
+        self.ws["drop_ctr"].copy_(snap["drop_ctr"])
+        self.pack_weights()
+
     def optimizer_state_dict(self):
         """AdamW state in `torch.optim.AdamW.state_dict()` layout ({'state': {i: {step, exp_avg, exp_avg_sq}},
         'param_groups': [...]}, parameters numbered in `named_parameters()` order) so that a checkpoint written through

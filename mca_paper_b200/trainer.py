@@ -129,13 +129,19 @@ class Trainer:
 
     def _capture(self):
         eng = self.eng
-        # warm-up on a side stream (allocations, attribute setting, NCCL init) before capture
+        # warm-up on a side stream (allocations, attribute setting, NCCL init) before capture; the two warm-up steps
+        # are real optimiser steps, so the training state is put back afterwards: N calls of step() == N updates.
+        # (Peer-memory mode: every rank's last action in a step is the barrier that publishes the parameter stores, so
+        # after the local synchronize nobody writes into this rank's buffers any more.)
+        snap = eng.snapshot_state()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
                 self._run_eager()
         torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        eng.restore_state(snap)
         torch.cuda.synchronize()
         if eng.world == 1 or eng._p2p is not None:
             # single GPU, or data parallel over peer memory (every exchange is one of our kernels): ONE graph

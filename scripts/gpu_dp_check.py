@@ -53,6 +53,23 @@ if rank == 0:
           f"param checksum {allc[0][1].item():.6f}", flush=True)
     assert same, "replicas diverged"
     assert all(l == l for l in losses), "NaN loss"
+# checkpoint under the sharded optimiser: save_state gathers the moment shards (collective), rank 0 writes accelerate's
+# directory layout; a perturbed trainer that loads it must reproduce the uninterrupted run's next step on every rank
+from mca_paper_b200 import checkpoint as K
+ckpt = "/tmp/mca_dp_ckpt"
+K.save_state(tr, ckpt)
+dist.barrier()
+s_next = float(tr.step(batch)[0])
+want = eng.flat.clone()
+tr.step(batch)                                   # move on, so that load_state has something to undo
+assert K.load_state(tr, ckpt) == 3
+assert abs(eng.lr_at(4) - 1e-4 * (3 * world) / 10.0) < 1e-10 or 3 * world >= 10   # scheduler walked `world` per step
+s_again = float(tr.step(batch)[0])
+torch.cuda.synchronize()
+rel = ((eng.flat - want).norm() / want.norm()).item()
+print(f"rank {rank}: resume loss {s_again:.6f} vs {s_next:.6f}, rel |dparams| {rel:.3e}", flush=True)
+assert abs(s_again - s_next) <= 2e-3 * abs(s_next) and rel < 1e-5, "resume from checkpoint differs"
+eng.check_p2p()
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:

@@ -195,6 +195,26 @@ def test_training_step_reduces_loss_and_matches_autograd_path():
     assert all(math.isfinite(x) for x in losses) and losses[-1] < losses[0]
 
 
+def test_graph_trainer_applies_one_update_per_step_call():
+    """The CUDA-graph trainer warms up with two real steps before capture; they must not count: after N calls of
+    step() the weights, moments and step counter equal those of the eager trainer after N updates."""
+    cfg = C.tiny_config("cmu", fcl=True)
+    kw = C.get_model_config(cfg)
+    batch = S.make_batch(cfg, seed=1, variant="dropout_ragged")
+    trainers = []
+    for graphs in (True, False):
+        torch.manual_seed(0)
+        model = MCA(**kw).to(dev)
+        tr = Trainer(model, lr=1e-3, clip=2.0, schedule="cosine", warmup_steps=2, total_steps=50, use_graphs=graphs)
+        for _ in range(3):
+            s = tr.step(batch)
+        trainers.append((tr, float(s[0])))
+    (tg, lg), (te, le) = trainers
+    assert int(tg.eng.step_dev.item()) == 3 and int(te.eng.step_dev.item()) == 3
+    ef, em = H.rel_err(tg.eng.flat, te.eng.flat), H.rel_err(tg.eng.exp_avg, te.eng.exp_avg)
+    assert abs(lg - le) <= 2e-3 * abs(le) and ef < 1e-3 and em < 1e-2, (lg, le, ef, em)   # atomics order only
+
+
 def test_patch_encoder_dropout_training_mode():
     """PatchEncoder's nn.Dropout (encoders.py:274): active only in training mode, keeps ~1-p of the elements scaled by
     1/(1-p), draws a new mask every forward, and the backward applies the SAME mask (dropped elements get no gradient:
