@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MCA_MAX_MODALITIES 8
+#define MCA_MAX_MODALITIES 32 /* modality blocks of the packed sequence (EAO replicates modalities per pass) */
 
 enum {
   MCA_OK = 0,
@@ -260,6 +260,18 @@ int mca_dp_adamw_shard(float* const* params_peers_dev, int world, int rank, cons
                        float* exp_avg_sq, long long shard_off, long long shard_n, const double* sumsq_slots,
                        long long* step_dev, float* total_norm_out, float grad_scale, const mca_adamw_cfg* cfg_host,
                        void* stream);
+
+/* ---- Mean pooling of the EAO baseline: MeanTokenProjectionPool(token_types=None, projection=False), model.py:235-280 as
+ * EAO.single_pass uses it (model.py:553-556,562-563).  x: bf16 [B, N, 512] final-normed tokens of all passes of a sample
+ * laid back to back; padding [B, N] bytes (non-zero = padded key); pass_start [R + 1] token offsets; pooled [B, R, 512] =
+ * mean of the live tokens of each pass (zeros when there are none, model.py:270-271); cnt [B, R] live counts (kept for
+ * the backward); scratch: mca_mean_pool_scratch_floats(B, R) floats.  Backward: dx [B, N, 512] fp32 =
+ * dpooled[b, tok_pass[t]] / cnt for live tokens, 0 for padded ones (tok_pass [N] = pass of every token). */
+int mca_mean_pool_scratch_floats(int B, int R);
+int mca_mean_pool_fwd(const void* x_bf16, const uint8_t* padding, const int* pass_start, int B, int N, int R, int d,
+                      float* pooled, float* cnt, float* scratch, void* stream);
+int mca_mean_pool_bwd(const float* dpooled, const uint8_t* padding, const int* tok_pass, const float* cnt, int B, int N,
+                      int R, int d, float* dx, void* stream);
 
 /* ---- Embedding-space evaluation metrics (utils/metrics.py; eval loop train_accel_gpu.py:136-184, infer_accel_gpu.py:115-147,
  * lp_accel_gpu.py:70-95).  All inputs fp32 row-major [rows, D] on the device; `scratch` holds at least

@@ -148,7 +148,7 @@ def named_config(name: str) -> Config:
 
 
 def tiny_config(kind: str = "cmu", zorro: bool = False, fcl: bool = True, bimodal: bool = False,
-                non_fusion_fcl: bool = False, layers: int = 2, batch_size: int = 8) -> Config:
+                non_fusion_fcl: bool = False, layers: int = 2, batch_size: int = 8, eao: bool = False) -> Config:
     """Reduced token counts (same d=512 geometry) so the CPU oracle finishes in seconds."""
     if kind == "cmu":
         enc = {
@@ -174,6 +174,9 @@ def tiny_config(kind: str = "cmu", zorro: bool = False, fcl: bool = True, bimoda
             "methylation": {"type": "TabularEncoder", "num_embeddings": 130, "max_tokens": 130, "max_value": 100},
             "mirna": {"type": "TabularEncoder", "num_embeddings": 64, "max_tokens": 64, "max_value": 100},
         }
+    extra = {}
+    if eao:  # the shipped *_EAO configs (configs/CMU_config1_EAO.yaml:17-28): pair passes, mean pooling, no fusion tokens
+        extra = dict(eao=True, no_fusion=True, mean_pool=True, fusion_combos=[2], fcl_root=[0, 1])
     return training_config(dict(_COMMON, encoder_configs=enc, num_fusion_tokens=22, layers=layers,
                                 batch_size=batch_size, bimodal_contrastive=bimodal, non_fusion_fcl=non_fusion_fcl,
-                                fcl=fcl, zorro=zorro))
+                                fcl=fcl, zorro=zorro, **extra))

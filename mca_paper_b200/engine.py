@@ -41,6 +41,7 @@ class Engine:
         self.N = plan.N
         self.M = self.B * self.N
         self.R = plan.R
+        self.eao = bool(getattr(plan, "eao", False))   # EAO baseline: passes stacked in one sequence, mean pooling
         self.device = None
         self.world, self.rank, self.group = 1, 0, None
         self._p2p = None
@@ -130,6 +131,8 @@ class Engine:
         self.kt_len = t(pl.tiles[:, 1].copy())
         self.n_kt = int(pl.tiles.shape[0])
         self.loss_plan = torch.from_numpy(pl.loss_plan.view(np.uint8).copy()).to(dev)
+        if self.eao:
+            self.pass_start, self.tok_pass = t(pl.pass_start), t(pl.tok_pass)
 
     # ------------------------------------------------------------------------------------------ weight layouts
     def _build_pack_descs(self, dev):
@@ -161,7 +164,8 @@ class Engine:
             add_matrix(p + "out", (D, D), [(p + "attn.to_out.weight", D, D, 0, 0, 0, 1.0)], M)
             add_matrix(p + "ff1", (2 * IP, D), [(p + "ff.feedforward.0.weight", 2 * I, D, 0, 1, I, 1.0)], M)
             add_matrix(p + "ff2", (D, IP), [(p + "ff.feedforward.2.weight", D, I, 0, 0, 0, 1.0)], M)
-        add_matrix("attn_pool.kv", (2 * D, D), [("attn_pool.to_kv.weight", 2 * D, D, 0, 0, 0, 1.0)], M)
+        if not self.eao:
+            add_matrix("attn_pool.kv", (2 * D, D), [("attn_pool.to_kv.weight", 2 * D, D, 0, 0, 0, 1.0)], M)
         self.enc_kpad = {}
         for name, enc in zip(self.plan.names, self.model.encoder_specs):
             pre = f"encoders.{name}."
@@ -220,16 +224,23 @@ class Engine:
         ws["x3_16"] = [b16(M, D) for _ in range(L)]
         ws["u"] = [b16(M, 2 * IP) for _ in range(L)]
         ws["h"] = [b16(M, IP) for _ in range(L)]
+        n_blk, blk_tok = len(self.plan.mask_src), int(sum(self.plan.mask_lengths))
         ws["y16"] = b16(M, D)    # branch output of out-proj / FF2 (consumed at once by the fused add + LayerNorm)
         ws["dy16"] = b16(M, D)   # branch gradient of the dX GEMMs (added inside the LayerNorm backward)
-        ws["stF"], ws["xf_16"], ws["kvp"] = f32(M, 2), b16(M, D), b16(M, 2 * D)
-        ws["qp"], ws["probs"], ws["fm"] = f32(R, D), f32(B, H, R, N), u8(B, R)
-        ws["po"], ws["pooled"] = f32(B, R, D), f32(B, R, D)
+        ws["stF"], ws["xf_16"] = f32(M, 2), b16(M, D)
+        ws["pooled"] = f32(B, R, D)
+        if self.eao:
+            ws["pool_cnt"] = f32(B, R)
+            ws["pool_scratch"] = f32(int(ops.fn("mca_mean_pool_scratch_floats")(B, R)))
+        else:
+            ws["kvp"] = b16(M, 2 * D)
+            ws["qp"], ws["probs"], ws["fm"] = f32(R, D), f32(B, H, R, N), u8(B, R)
+            ws["po"] = f32(B, R, D)
         ws["vmean"] = torch.zeros(B, D, device=dev, dtype=torch.float32)
         # offsets / masks
-        ws["padding"], ws["pad_mod"] = u8(B, N), u8(B * self.plan.n_tok)
-        ws["present"], ws["live_count"] = u8(B, self.plan.n_mod), i32(B, self.plan.n_mod)
-        ws["live_idx"], ws["cu_live"] = i32(B, N), i32(B * self.plan.n_mod + 1)
+        ws["padding"], ws["pad_mod"] = u8(B, N), u8(B * blk_tok)
+        ws["present"], ws["live_count"] = u8(B, n_blk), i32(B, n_blk)   # the first n_mod columns are the modalities
+        ws["live_idx"], ws["cu_live"] = i32(B, N), i32(B * n_blk + 1)
         ws["kt_class"], ws["any_absent"], ws["nonfinite"] = u8(B, self.n_kt), i32(1), i32(1)
         ws["kt_live"] = i32(B, self.n_kt, 4)
         # encoders
@@ -259,8 +270,10 @@ class Engine:
         ws["dx_a"], ws["dx_b"], ws["d16"] = f32(M, D), f32(M, D), b16(M, D)
         ws["du"], ws["dattn"], ws["dqkv"] = b16(M, 2 * IP), b16(M, D), b16(M, 3 * D)
         ws["dq_acc"], ws["delta"], ws["ucorr"] = f32(M, D), f32(B, H, N), f32(B, D)
-        ws["dkvp"], ws["dxf"] = b16(M, 2 * D), f32(M, D)
-        ws["pool_ds"], ws["dqp"], ws["dpo"] = f32(B, H, R, N), f32(R, D), f32(B, R, D)
+        ws["dxf"] = f32(M, D)
+        if not self.eao:
+            ws["dkvp"] = b16(M, 2 * D)
+            ws["pool_ds"], ws["dqp"], ws["dpo"] = f32(B, H, R, N), f32(R, D), f32(B, R, D)
         self.ws = ws
         self._gather_ws = None
         self._ws_ready = True
@@ -372,10 +385,12 @@ class Engine:
             if m.shape != (self.B, L):
                 raise AssertionError(f"attention_mask shape {tuple(m.shape)} != {(self.B, L)} (batch must equal batch_size, model.py:454)")
         self._mask_keepalive = [m if m.is_contiguous() else m.contiguous() for m in masks]
-        n = pl.n_mod
-        ptrs = (ctypes.c_void_p * n)(*[m.data_ptr() for m in self._mask_keepalive])
-        es = (ctypes.c_int * n)(*[m.element_size() for m in self._mask_keepalive])
-        lens = (ctypes.c_int * n)(*pl.lengths)
+        # one entry per modality block of the packed sequence (EAO: a modality pads every pass it takes part in)
+        blocks = [self._mask_keepalive[src] for src in pl.mask_src]
+        n = len(blocks)
+        ptrs = (ctypes.c_void_p * n)(*[m.data_ptr() for m in blocks])
+        es = (ctypes.c_int * n)(*[m.element_size() for m in blocks])
+        lens = (ctypes.c_int * n)(*pl.mask_lengths)
         call("mca_build_offsets", ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(es, ctypes.c_void_p),
              ctypes.cast(lens, ctypes.c_void_p), n, self.B, self.N, P(self.kt_start), P(self.kt_len), self.n_kt,
              P(ws["padding"]), P(ws["pad_mod"]), P(ws["present"]), P(ws["live_count"]), P(ws["live_idx"]),
@@ -487,6 +502,11 @@ class Engine:
                 raise NotImplementedError(f"unknown encoder type {enc['type']}")
         if pl.F:
             call("mca_broadcast_rows", P(self.pview("fusion_tokens")), P(x0), pl.F, D, self.B, self.N, pl.n_tok, S())
+        if self.eao:
+            # every modality is encoded once (model.py:576-578); the passes it takes part in read replicas (model.py:584)
+            xv = x0.view(self.B, self.N, D)
+            for dst, src, L in pl.replicas:
+                xv[:, dst:dst + L].copy_(xv[:, src:src + L])
 
     def _dropout(self, i, enc, rows32):
         """nn.Dropout of PatchEncoder (encoders.py:274) on the modality's rows of `rows32` (tokens in the forward, their
@@ -534,6 +554,11 @@ class Engine:
             else:
                 ops.add_layernorm512_fwd(ws["x2"][l], ws["st2"][l], gamma, beta, ws["y16"], ws["xa"][l + 1],
                                          self.pview("norm.gamma"), self.model.norm.beta, ws["xf_16"], ws["stF"], M)
+        if self.eao:
+            # mean pooling of every pass over its live tokens (model.py:562-563, 257-280)
+            call("mca_mean_pool_fwd", P(ws["xf_16"]), P(ws["padding"]), P(self.pass_start), self.B, self.N, self.R, D,
+                 P(ws["pooled"]), P(ws["pool_cnt"]), P(ws["pool_scratch"]), S())
+            return ws["pooled"]
         # attention pooling on the final-normed tokens (model.py:470-473)
         ops.gemm(ws["xf_16"], 0, self.W("attn_pool.kv"), 0, M, 2 * D, D, _lib.EPI_BF16, ws["kvp"])
         rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
@@ -565,7 +590,7 @@ class Engine:
             pooled_all = pooled
         self._pooled_all = pooled_all
         call("mca_contrastive_allpairs_fwd", P(pooled_all), P(ws["present"]), P(self.loss_plan), self.plan.n_pairs, P(s),
-             self.B, self.world * self.B, self.R, D, self.plan.n_mod, self.rank, lo, hi,
+             self.B, self.world * self.B, self.R, D, len(self.plan.mask_src), self.rank, lo, hi,
              P(ws["losses"]), P(ws["summary"]), P(ws["w_default"]), S())
         return ws["losses"], ws["summary"]
 
@@ -581,7 +606,7 @@ class Engine:
             g["dscale"].zero_()
             s = self.pview("loss.loss_fn.logit_scale")
             call("mca_contrastive_allpairs_bwd", P(self._pooled_all), P(ws["present"]), P(self.loss_plan),
-                 self.plan.n_pairs, P(s), self.B, GB, self.R, D, self.plan.n_mod, self.rank, P(w), P(p["dpooled_all"]),
+                 self.plan.n_pairs, P(s), self.B, GB, self.R, D, len(self.plan.mask_src), self.rank, P(w), P(p["dpooled_all"]),
                  P(g["dscale"]), S())
             self.xgpu_barrier()
             n = self.B * self.R * D
@@ -593,7 +618,7 @@ class Engine:
         g["dscale"].zero_()
         s = self.pview("loss.loss_fn.logit_scale")
         call("mca_contrastive_allpairs_bwd", P(self._pooled_all), P(ws["present"]), P(self.loss_plan), self.plan.n_pairs,
-             P(s), self.B, GB, self.R, D, self.plan.n_mod, self.rank, P(w), P(dall), P(g["dscale"]), S())
+             P(s), self.B, GB, self.R, D, len(self.plan.mask_src), self.rank, P(w), P(dall), P(g["dscale"]), S())
         if self.world > 1:
             torch.distributed.reduce_scatter_tensor(g["dpooled"], dall, op=torch.distributed.ReduceOp.SUM, group=self.group)
         self.gview("loss.loss_fn.logit_scale").add_(g["dscale"].view(()))
@@ -608,8 +633,21 @@ class Engine:
     def trunk_backward(self, dpooled):
         """Reverse of trunk_forward; parameter gradients land in self.flat_grad (state_dict layout)."""
         ws, pl, M, IP, B, R, H, N = self.ws, self.plan, self.M, self.IP, self.B, self.R, self.H, self.N
-        rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
         self.garena.zero_()  # every dW GEMM reduce-adds its k-splits into this arena
+        if self.eao:
+            call("mca_mean_pool_bwd", P(dpooled), P(ws["padding"]), P(self.tok_pass), P(ws["pool_cnt"]), B, N, R, D,
+                 P(ws["dxf"]), S())
+        else:
+            self._pool_backward(dpooled)
+        dx, dx_alt = ws["dx_a"], ws["dx_b"]
+        ops.layernorm512_bwd(ws["dxf"], ws["xa"][self.depth], ws["stF"], self.pview("norm.gamma"), dx, ws["d16"],
+                             self.gview("norm.gamma"), None, M)
+        self._layers_backward(dx, dx_alt)
+
+    def _pool_backward(self, dpooled):
+        """Attention pooling backward (model.py:470-473): gradients of return_tokens / attn_pool.* and dxf."""
+        ws, M, B, R, H, N = self.ws, self.M, self.B, self.R, self.H, self.N
+        rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
         dp2 = dpooled.reshape(B * R, D)
         po2 = ws["po"].view(B * R, D)
         # pooled = po Wo^T + rt
@@ -624,9 +662,9 @@ class Engine:
         # through the K/V projection and the final LayerNorm
         ops.gemm(ws["dkvp"], 0, self.W("attn_pool.kv"), 1, M, D, 2 * D, _lib.EPI_F32, ws["dxf"])
         self._dw("attn_pool.kv", ws["dkvp"], ws["xf_16"], 2 * D, D, M)
-        dx, dx_alt = ws["dx_a"], ws["dx_b"]
-        ops.layernorm512_bwd(ws["dxf"], ws["xa"][self.depth], ws["stF"], self.pview("norm.gamma"), dx, ws["d16"],
-                             self.gview("norm.gamma"), None, M)
+
+    def _layers_backward(self, dx, dx_alt):
+        ws, M, IP = self.ws, self.M, self.IP
         for l in reversed(range(self.depth)):
             p = f"layers.{l}."
             gamma, dgamma = self.pview(p + "norm.gamma"), self.gview(p + "norm.gamma")
@@ -647,6 +685,11 @@ class Engine:
             self._dw(p + "qkv", ws["dqkv"], ws["x1_16"][l], 3 * D, D, M)
             ops.layernorm512_bwd(dx, ws["xa"][l], ws["st1"][l], gamma, dx_alt, ws["d16"], dgamma, None, M, dy_delta=ws["dy16"])
             dx, dx_alt = dx_alt, dx
+        if self.eao:
+            # the gradient of a modality's tokens is the sum over every pass that read them
+            dv = dx.view(self.B, self.N, D)
+            for dst, src, L in self.plan.replicas:
+                dv[:, src:src + L].add_(dv[:, dst:dst + L])
         self.encode_backward(dx)
         call("mca_unpack_grads", P(self.flat_grad), P(self.garena), P(self.unpack_descs), self.n_desc, S())
 

@@ -20,7 +20,7 @@ from torch import nn
 from . import _lib
 from .encoders import encoders_dict
 from .engine import D, Engine
-from .plan import FUSION_TOKEN, GLOBAL_TOKEN, StaticPlan, fusion_channel_sets
+from .plan import FUSION_TOKEN, GLOBAL_TOKEN, EAOPlan, StaticPlan, fusion_channel_sets
 from .utils.contrastive_loss_with_temperature import ContrastiveLossWithTemperature
 
 
@@ -149,7 +149,49 @@ class _MCAFunction(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
-class MCA(nn.Module):
+class _FusedModel(nn.Module):
+    """forward() shared by MCA / MMA and EAO: one autograd node around the fused engine, outputs named by the plan."""
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine
+
+    def _named_outputs(self, pooled):
+        return {key: pooled[:, row, :] for key, row in self.plan.output_rows}
+
+    def forward(self, batch, no_loss=False):
+        eng = self._engine
+        eng.ensure_flat()
+        # data parallel without the fused Trainer (the reference loop: model(batch); loss.backward() under DDP): the loss
+        # gathers the pooled embeddings across the default process group like gather_tensor does (utils/distributed.py:
+        # 23-56), through NCCL — the peer-memory exchange is set up by Trainer / Engine.set_distributed(p2p=True)
+        if (eng.world == 1 and torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1 and torch.distributed.get_backend() == "nccl"):
+            eng.set_distributed(torch.distributed.get_world_size(), torch.distributed.get_rank(), None, p2p=False)
+        eng.pack_weights()
+        params = [p for _, p in eng._param_list()]
+        want_loss = not no_loss
+        pooled, losses, summary = _MCAFunction.apply(self, batch, want_loss, *params)
+        if self.check_finite:
+            flag = int(eng.ws["nonfinite"].item())
+            if flag & 2:
+                raise IndexError("index out of range in self")  # what nn.Embedding raises for a bad token / index
+            if flag & 1:
+                raise Exception("Tokens are not finite")  # encoders.py:197-198
+        out = self._named_outputs(pooled)
+        present = eng.ws["present"].clone().to(torch.bool)
+        sample_mask = {name: present[:, i] for i, name in enumerate(self.modality_types)}
+        if want_loss:
+            out["losses"] = {name: losses[i] for i, name in enumerate(self.plan.loss_names)}
+            if self.plan.do_fcl:
+                out["fcl_loss"] = summary[1]
+                out["no-fcl_loss"] = summary[2]
+            out["loss"] = summary[0]
+        out["modality_sample_mask"] = sample_mask
+        return out
+
+
+class MCA(_FusedModel):
     def __init__(self, encoder_configs, dim, depth, dim_head=64, heads=8, ff_mult=4, num_fusion_tokens=16,
                  batch_size=8, return_padding=False, return_logits=False, bimodal_contrastive=False,
                  non_fusion_fcl=False, fcl=False, fcl_root=(1, 2, 3, 4, 5), fusion_combos=(4, 5), zorro=False,
@@ -195,41 +237,46 @@ class MCA(nn.Module):
         self._engine = Engine(self, plan, depth, heads, ff_inner, batch_size)
         self.check_finite = True
 
-    # -------------------------------------------------------------------------------------------------------
-    @property
-    def engine(self) -> Engine:
-        return self._engine
 
-    def _named_outputs(self, pooled):
-        return {key: pooled[:, row, :] for key, row in self.plan.output_rows}
+class EAO(_FusedModel):
+    """The "everything at once" baseline with the reference's constructor and state_dict (model.py:481-596): the same
+    MCALayer stack is run once per modality and once per modality combination, each pass mean-pooled, the pooled tokens
+    contrasted pairwise (train_accel_gpu.py:51-52 selects it with `eao: true`; every shipped *_EAO config has
+    no_fusion=True, mean_pool=True).  All passes of a sample run as ONE packed sequence with a block-diagonal mask
+    (plan.EAOPlan) through the same kernels as MCA; there are no fusion tokens, return tokens or pooling weights."""
 
-    def forward(self, batch, no_loss=False):
-        eng = self._engine
-        eng.ensure_flat()
-        # data parallel without the fused Trainer (the reference loop: model(batch); loss.backward() under DDP): the loss
-        # gathers the pooled embeddings across the default process group like gather_tensor does (utils/distributed.py:
-        # 23-56), through NCCL — the peer-memory exchange is set up by Trainer / Engine.set_distributed(p2p=True)
-        if (eng.world == 1 and torch.distributed.is_available() and torch.distributed.is_initialized()
-                and torch.distributed.get_world_size() > 1 and torch.distributed.get_backend() == "nccl"):
-            eng.set_distributed(torch.distributed.get_world_size(), torch.distributed.get_rank(), None, p2p=False)
-        eng.pack_weights()
-        params = [p for _, p in eng._param_list()]
-        want_loss = not no_loss
-        pooled, losses, summary = _MCAFunction.apply(self, batch, want_loss, *params)
-        if self.check_finite:
-            flag = int(eng.ws["nonfinite"].item())
-            if flag & 2:
-                raise IndexError("index out of range in self")  # what nn.Embedding raises for a bad token / index
-            if flag & 1:
-                raise Exception("Tokens are not finite")  # encoders.py:197-198
-        out = self._named_outputs(pooled)
-        present = eng.ws["present"].clone().to(torch.bool)
-        sample_mask = {name: present[:, i] for i, name in enumerate(self.modality_types)}
-        if want_loss:
-            out["losses"] = {name: losses[i] for i, name in enumerate(self.plan.loss_names)}
-            if self.plan.do_fcl:
-                out["fcl_loss"] = summary[1]
-                out["no-fcl_loss"] = summary[2]
-            out["loss"] = summary[0]
-        out["modality_sample_mask"] = sample_mask
-        return out
+    def __init__(self, encoder_configs, dim, depth, dim_head=64, heads=8, ff_mult=4, num_fusion_tokens=16,
+                 batch_size=8, return_padding=False, return_logits=False, bimodal_contrastive=False,
+                 non_fusion_fcl=False, fcl=False, fcl_root=(1, 2, 3, 4, 5), fusion_combos=(4, 5), zorro=False,
+                 no_fusion=True, mean_pool=True, **kwargs):
+        super().__init__()
+        if not mean_pool:
+            raise NotImplementedError("EAO(mean_pool=False) cannot run in the reference either: single_pass reads "
+                                      "self.pool_mask, which EAO never defines (model.py:560)")
+        if dim != D:
+            raise AssertionError("encoders hard-wire embedding_dim=512 (encoders.py:79,104,151,178,230): dim must be 512")
+        encoder_configs = {k: dict(v) for k, v in dict(encoder_configs).items()}
+        self.batch_size = batch_size
+        plan = EAOPlan(encoder_configs, list(fusion_combos), fcl, zorro, no_fusion, bimodal_contrastive, non_fusion_fcl)
+        self.plan = plan
+        self.fusion_combos = plan.combos
+        self.fcl_root = None                                   # model.py:506
+        self.fusion_token = FUSION_TOKEN
+        self.return_token_types = plan.return_token_types
+        self.max_return_tokens = len(plan.return_token_types)
+        self.register_buffer("return_token_types_tensor", torch.tensor(plan.return_token_types), persistent=False)
+        self.heads = heads
+        self.return_padding, self.return_logits = return_padding, return_logits
+        # same construction order as the reference (model.py:520-565): a seeded init draws the same stream
+        self.encoders = nn.ModuleDict({name: encoders_dict[cfg["type"]](**cfg) for name, cfg in encoder_configs.items()})
+        self.modality_types = list(encoder_configs.keys())
+        self.encoder_specs = [dict(cfg) for cfg in encoder_configs.values()]
+        self.token_dims = plan.lengths
+        self.layers = nn.ModuleList([MCALayer(dim, dim_head, heads, ff_mult) for _ in range(depth)])
+        self.norm = LayerNorm(dim)
+        self.register_buffer("token_types", torch.from_numpy(plan.token_types.copy()))
+        self.return_tokens = None
+        self.loss = MCAPretrainingLoss(self.modality_types, plan)
+        ff_inner = self.layers[0].ff.inner_dim if depth else int(dim * ff_mult * 2 / 3)
+        self._engine = Engine(self, plan, depth, heads, ff_inner, batch_size)
+        self.check_finite = True

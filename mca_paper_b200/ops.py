@@ -59,6 +59,9 @@ _SIGS = {
     "mca_embedding_scatter_add": [VP, VP, I32, I32, I32, I32, I32, I32, I32, VP, VP],
     "mca_patchify": [VP, I32, I32, I32, I32, I32, F32, VP, VP, VP],
     "mca_dropout_rows": [VP, I32, I32, I32, I32, I32, F32, C.c_uint64, VP, VP],
+    "mca_mean_pool_scratch_floats": [I32, I32],
+    "mca_mean_pool_fwd": [VP, VP, VP, I32, I32, I32, I32, VP, VP, VP, VP],
+    "mca_mean_pool_bwd": [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP],
     "mca_row_inv_norms": [VP, I64, I32, F32, VP, VP],
     "mca_alignment": [VP, VP, I64, I32, F32, I32, VP, VP, VP],
     "mca_uniformity": [VP, I64, I32, F32, I32, VP, VP, VP, VP],
@@ -99,7 +102,7 @@ def S():
 # kernels launched by each entry point (memsets not counted) — bench.py reports the per-step total
 KERNELS_PER_CALL = {"mca_build_offsets": 2, "mca_attn_fwd": 2, "mca_attn_bwd": 3, "mca_pool_attn_bwd": 2,
                     "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3, "mca_dp_adamw_shard": 2,
-                    "mca_embedding_renorm_indexed": 2, "mca_alignment": 2, "mca_uniformity": 3, "mca_retrieval_ranks": 4}
+                    "mca_embedding_renorm_indexed": 2, "mca_mean_pool_fwd": 2, "mca_alignment": 2, "mca_uniformity": 3, "mca_retrieval_ranks": 4}
 COUNT = {"n": 0}
 PROFILE = {"on": False, "events": []}
 RECORD = {"on": False, "calls": []}  # (name, tag, args) of every entry-point call, for isolated device timing

@@ -35,6 +35,9 @@ class StaticPlan:
             raise AssertionError("at most 8 modalities are supported")
         self.lengths = [int(encoder_configs[k]["max_tokens"]) for k in self.names]
         self.offsets = [int(x) for x in np.cumsum([0] + self.lengths[:-1])]
+        self.eao = False
+        self.mask_src = list(range(self.n_mod))      # (virtual) modality blocks of the packed sequence: which
+        self.mask_lengths = list(self.lengths)        # modality's attention_mask pads them, and their lengths
         self.zorro, self.fcl, self.no_fusion = bool(zorro), bool(fcl), bool(no_fusion)
         self.do_fcl = self.fcl and not self.zorro
         self.F = 0 if no_fusion else int(num_fusion_tokens)
@@ -112,10 +115,14 @@ class StaticPlan:
         self._build_loss_plan(bimodal_contrastive, non_fusion_fcl)
 
     # ------------------------------------------------------------------------------------------------ tiles
-    def _build_tiles(self):
+    def _segments(self):
         segs = [(o, n) for o, n in zip(self.offsets, self.lengths)]
         if self.F:
             segs.append((self.n_tok, self.F))
+        return segs
+
+    def _build_tiles(self):
+        segs = self._segments()
         tiles = []
         for o, n in segs:
             for s in range(o, o + n, TILE):
@@ -198,3 +205,79 @@ class StaticPlan:
             arr[i] = (p[1], p[2], p[3], p[4], p[5])
         self.loss_plan = arr
         self.n_pairs = len(plan)
+
+
+class EAOPlan(StaticPlan):
+    """Static tables of the `EAO` ("everything at once") baseline, model.py:481-596: the SAME layers are run once per
+    modality and once per modality combination, each pass over the packed tokens of its modalities with key padding
+    as the only mask (model.py:544-545,583-587), then mean-pooled (MeanTokenProjectionPool, model.py:257-280).
+
+    Here all passes of a sample are laid out back to back as ONE sequence of N = sum(pass lengths) tokens with a
+    block-diagonal static mask (a token attends exactly the tokens of its own pass), which is what the block-sparse
+    attention kernels and the token-parallel GEMM / LayerNorm kernels already execute: the single-modality passes come
+    first, so the first n_tok tokens are the encoder outputs in modality order and every later block is a replica of one
+    of them (`replicas`: (dst offset, src offset, length)).  Key group = block index (<= 32 blocks); `mask_src` lists,
+    per block, the modality whose attention_mask pads it.  A row whose pass has no live key at all is never read by
+    the pooling (its pooled token is zeros, model.py:270-271), so the fully-masked-row rule needs no per-pass variant.
+    Pooled rows are [modalities..., combinations...] = the row map of MCAPretrainingLoss with no_fusion (model.py:181-186).
+    """
+
+    def __init__(self, encoder_configs: dict, fusion_combos, fcl: bool, zorro: bool, no_fusion: bool,
+                 bimodal_contrastive: bool, non_fusion_fcl: bool):
+        self.names = list(encoder_configs.keys())
+        self.n_mod = len(self.names)
+        if self.n_mod > 8:
+            raise AssertionError("at most 8 modalities are supported")
+        if not no_fusion:
+            # EAO pools no fusion row, so MCAPretrainingLoss would index a pooled token that does not exist (model.py:190)
+            raise NotImplementedError("EAO is only defined with no_fusion=True (every shipped *_EAO config)")
+        self.eao = True
+        self.lengths = [int(encoder_configs[k]["max_tokens"]) for k in self.names]
+        self.offsets = [int(x) for x in np.cumsum([0] + self.lengths[:-1])]
+        self.zorro, self.fcl, self.no_fusion = bool(zorro), bool(fcl), True
+        self.do_fcl = self.fcl and not self.zorro
+        self.F = 0
+        self.n_tok = int(sum(self.lengths))
+        self.combos = fusion_channel_sets(self.n_mod, fusion_combos)
+        self.passes = [[i] for i in range(self.n_mod)] + [sorted(c) for c in self.combos]   # model.py:583
+        self.R = len(self.passes)
+        self.return_token_types = list(range(self.n_mod))                                   # model.py:512
+        self.token_types = np.concatenate([np.full(n, i, dtype=np.int64) for i, n in enumerate(self.lengths)])
+
+        mask_src, mask_lengths, blk_off, pass_of_blk, pass_start = [], [], [], [], [0]
+        off = 0
+        for pi, members in enumerate(self.passes):
+            for m in members:
+                mask_src.append(m)
+                mask_lengths.append(self.lengths[m])
+                blk_off.append(off)
+                pass_of_blk.append(pi)
+                off += self.lengths[m]
+            pass_start.append(off)
+        self.mask_src, self.mask_lengths, self.block_offsets = mask_src, mask_lengths, blk_off
+        self.pass_start = np.asarray(pass_start, dtype=np.int32)
+        self.N = off
+        self.n_groups = len(mask_src)
+        if self.n_groups > 32:
+            raise AssertionError("more than 32 key groups (modality blocks over all passes)")
+        self.replicas = [(blk_off[g], self.offsets[mask_src[g]], mask_lengths[g]) for g in range(self.n_mod, self.n_groups)]
+
+        keygrp = np.zeros(self.N, dtype=np.uint8)
+        rowbits = np.zeros(self.N, dtype=np.uint32)
+        tok_pass = np.zeros(self.N, dtype=np.int32)
+        pass_bits = [0] * self.R
+        for g, pi in enumerate(pass_of_blk):
+            pass_bits[pi] |= 1 << g
+        for g, (o, n, pi) in enumerate(zip(blk_off, mask_lengths, pass_of_blk)):
+            keygrp[o:o + n] = g
+            rowbits[o:o + n] = np.uint32(pass_bits[pi])
+            tok_pass[o:o + n] = pi
+        self.keygrp, self.rowbits, self.tok_pass = keygrp, rowbits, tok_pass
+        self.pool_rowbits = np.asarray(pass_bits, dtype=np.uint32)      # pooled row p reads the tokens of pass p
+        self.attn_mask = tok_pass[:, None] != tok_pass[None, :]          # True = may not attend (never registered as a buffer)
+        self.pool_mask = np.arange(self.R)[:, None] != tok_pass[None, :]
+        self._build_tiles()
+        self._build_loss_plan(bimodal_contrastive, non_fusion_fcl)
+
+    def _segments(self):
+        return list(zip(self.block_offsets, self.mask_lengths))

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from mca_paper_b200 import config as C, synthetic as S  # noqa: E402
-from mca_paper_b200.model import MCA  # noqa: E402
+from mca_paper_b200.model import EAO, MCA  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
@@ -34,6 +34,9 @@ CASES = {
     "tiny_tcga_all_losses": dict(cfg=("tcga", dict(fcl=True, bimodal=True, non_fusion_fcl=True)), variant="tcga", seed=1),
     # SequenceEncoder + SparseTabularEncoder + PatchEncoder + EmbeddedSequenceEncoder, ragged / absent modalities
     "tiny_mixed_encoders": dict(cfg=("mixed", dict(fcl=True)), variant="dropout_ragged", seed=3),
+    # EAO baseline (model.py:481-596) as the shipped *_EAO configs run it: 4 single + 6 pair passes, mean pooling,
+    # 6 modality pairs + 20 fcl_<modality>|<pair> losses; ragged lengths and absent modalities
+    "tiny_cmu_eao": dict(cfg=("cmu", dict(fcl=True, bimodal=True, non_fusion_fcl=True, eao=True)), variant="dropout_ragged", seed=1),
 }
 FULL_GRADS = ["return_tokens", "fusion_tokens", "norm.gamma", "layers.0.norm.gamma", "loss.loss_fn.logit_scale",
               "layers.1.norm.gamma"]
@@ -68,7 +71,7 @@ def make_case(name, spec):
     cfg = C.tiny_config(kind, **kwargs)
     kw = C.get_model_config(cfg)
     torch.manual_seed(0)
-    mine = MCA(**kw)
+    mine = (EAO if kw.get("eao") else MCA)(**kw)
     sd = {k: v.detach().clone() for k, v in mine.state_dict().items()}
     ref = ref_shim.build_reference_model(kw, state_dict=sd)  # strict load: schema parity
     batch = S.make_batch(cfg, seed=spec["seed"], variant=spec["variant"])
@@ -237,8 +240,10 @@ def main():
         raise SystemExit("the live reference is not present; golden fixtures can only be regenerated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else ""
-    if only in ("", "cases"):
+    if only in ("", "cases") or only.startswith("case:"):
         for name, spec in CASES.items():
+            if only.startswith("case:") and name != only[5:]:
+                continue
             make_case(name, spec)
     if only in ("", "static"):
         make_static()

@@ -418,6 +418,65 @@ def mca_forward(sd: dict, spec: dict, batch: dict, no_loss: bool = False, tables
     return out
 
 
+def mean_token_pool(x, key_padding_mask):
+    """MeanTokenProjectionPool(token_types_tensor=None, projection=False) as EAO builds it (model.py:553-556, forward
+    :257-280): one output token per sample = mean of the rows that are not padded, zeros when there are none; the
+    projection is an Identity.  Returns [B, 1, d]."""
+    rows = []
+    for i in range(x.shape[0]):
+        v = x[i, ~key_padding_mask[i], :]
+        rows.append(torch.zeros(x.shape[2], dtype=x.dtype) if v.shape[0] == 0 else v.mean(dim=0))
+    out = torch.stack(rows).unsqueeze(1)
+    if out.isnan().any():
+        raise Exception(f"NaN in output from Mean Pooling {int(out.isnan().sum())}, could be from any place before this")
+    return out
+
+
+def eao_passes(spec: dict, tables: Optional[dict] = None):
+    """model.py:583: one pass per modality, then one per fusion combination (adjusted_powerset order)."""
+    t = tables or static_tables(spec)
+    return [[i] for i in range(len(t["names"]))] + [sorted(c) for c in t["combos"]]
+
+
+def eao_trunk(sd: dict, spec: dict, batch: dict, tables: Optional[dict] = None):
+    """EAO.forward model.py:567-590 ("everything at once" baseline): every modality is encoded once; each pass packs the
+    tokens of its modalities, runs the SAME layers with no static mask (key padding only, model.py:544-545), the final
+    norm and the mean pooling; the pooled tokens of all passes are concatenated."""
+    t = tables or static_tables(spec)
+    heads = int(spec.get("heads", 8))
+    toks, masks = [], []
+    for name in t["names"]:
+        x, m = encode_modality(sd, name, spec["encoder_configs"][name], batch[name])
+        toks.append(x)
+        masks.append(m)
+    sample_mask = {k: (m == 0).sum(dim=1) != 0 for k, m in zip(t["names"], masks)}  # model.py:580
+    pooled = []
+    for members in eao_passes(spec, t):
+        x = torch.cat([toks[i] for i in members], dim=1)
+        padding = torch.cat([masks[i] for i in members], dim=1).to(torch.bool)
+        for l in range(int(spec["depth"])):
+            p = f"layers.{l}."
+            g, bta = sd[p + "norm.gamma"], sd[p + "norm.beta"]
+            x = gamma_norm(x, g, bta)
+            x = masked_attention(x, None, sd[p + "attn.to_q.weight"], sd[p + "attn.to_kv.weight"],
+                                 sd[p + "attn.to_out.weight"], heads, None, padding) + x
+            x = gamma_norm(x, g, bta)
+            x = geglu_ff(x, sd[p + "ff.feedforward.0.weight"], sd[p + "ff.feedforward.2.weight"]) + x
+        x = gamma_norm(x, sd["norm.gamma"], sd["norm.beta"])
+        pooled.append(mean_token_pool(x, padding))
+    return torch.cat(pooled, dim=1), sample_mask
+
+
+def eao_forward(sd: dict, spec: dict, batch: dict, no_loss: bool = False, tables=None):
+    """Whole EAO.forward (model.py:567-596): the pooled rows are [modalities..., combinations...], which is the row map
+    of MCAPretrainingLoss with no_fusion=True (model.py:181-186), i.e. loss_plan() of the same spec."""
+    t = tables or static_tables(spec)
+    pooled, sample_mask = eao_trunk(sd, spec, batch, t)
+    out = pretraining_loss(pooled, sample_mask, sd["loss.loss_fn.logit_scale"], spec, t, no_loss=no_loss)
+    out["modality_sample_mask"] = sample_mask
+    return out
+
+
 def mca_forward_ranks(sd: dict, spec: dict, batches: List[dict], tables=None):
     """Single-process emulation of G data-parallel ranks: rank r scores its rows against the
     concatenated columns of every rank; summing the returned per-rank losses and back-propagating gives the

@@ -79,7 +79,7 @@ def build_reference_model(model_kwargs: dict, state_dict=None):
     """Construct reference MCA(**model_kwargs) (stdout noise suppressed) and optionally load a state_dict."""
     ref = load_reference()
     with contextlib.redirect_stdout(open(os.devnull, "w")):
-        m = ref.MCA(**model_kwargs)
+        m = (ref.EAO if model_kwargs.get("eao") else ref.MCA)(**model_kwargs)  # train_accel_gpu.py:47-52
     if state_dict is not None:
         m.load_state_dict(state_dict, strict=True)
     return m

@@ -5,7 +5,7 @@ import os
 import torch
 
 from mca_paper_b200 import config as C, synthetic as S
-from mca_paper_b200.model import MCA
+from mca_paper_b200.model import EAO, MCA
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -17,6 +17,8 @@ CASES = {
     "tiny_tcga_all_losses": dict(cfg=("tcga", dict(fcl=True, bimodal=True, non_fusion_fcl=True)), variant="tcga", seed=1),
     # SequenceEncoder + SparseTabularEncoder + PatchEncoder + EmbeddedSequenceEncoder, ragged / absent modalities
     "tiny_mixed_encoders": dict(cfg=("mixed", dict(fcl=True)), variant="dropout_ragged", seed=3),
+    # EAO baseline (model.py:481-596): 4 single + 6 pair passes, mean pooling, 26 losses
+    "tiny_cmu_eao": dict(cfg=("cmu", dict(fcl=True, bimodal=True, non_fusion_fcl=True, eao=True)), variant="dropout_ragged", seed=1),
 }
 
 
@@ -47,10 +49,16 @@ def build_case(name):
     cfg = C.tiny_config(kind, **kwargs)
     kw = C.get_model_config(cfg)
     torch.manual_seed(0)
-    model = MCA(**kw)
+    model = (EAO if kw.get("eao") else MCA)(**kw)   # train_accel_gpu.py:47-52
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     batch = S.make_batch(cfg, seed=spec["seed"], variant=spec["variant"])
     return cfg, kw, model, sd, batch
+
+
+def oracle_forward(kw):
+    """The oracle entry point of the model family the kwargs select."""
+    from oracle import mca_oracle as O
+    return O.eao_forward if kw.get("eao") else O.mca_forward
 
 
 def key_to_str(k):

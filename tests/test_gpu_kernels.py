@@ -501,3 +501,42 @@ def test_pack_unpack_roundtrip():
     call("mca_unpack_grads", P(eng.flat_grad), P(eng.garena), P(eng.unpack_descs), eng.n_desc, stream())
     got = eng.gview("layers.0.ff.feedforward.0.weight")
     assert rel_err(got, w1) < 4e-3
+
+
+@pytest.mark.parametrize("B,starts", [(3, [0, 5, 5, 300, 1000]), (8, [0, 150, 195, 265, 285, 480, 700])])
+def test_mean_pool_fwd_bwd_match_torch(B, starts):
+    """mca_mean_pool_fwd / _bwd (MeanTokenProjectionPool as EAO uses it, model.py:257-280,553-563) against torch: per
+    pass mean over the live tokens, zeros for a pass without any (and for an empty pass), gradient 1/count on live rows."""
+    torch.manual_seed(B)
+    N, R = starts[-1], len(starts) - 1
+    x = torch.randn(B, N, 512, device=dev).to(torch.bfloat16)
+    pad = torch.rand(B, N, device=dev) < 0.3
+    pad[0, starts[0]:starts[1]] = True                      # a pass with no live token
+    if B > 1:
+        pad[1] = False
+    pad8 = pad.to(torch.uint8).contiguous()
+    ps = torch.tensor(starts, device=dev, dtype=torch.int32)
+    tok_pass = torch.zeros(N, device=dev, dtype=torch.int32)
+    for r in range(R):
+        tok_pass[starts[r]:starts[r + 1]] = r
+    pooled, cnt = torch.empty(B, R, 512, device=dev), torch.empty(B, R, device=dev)
+    scratch = torch.empty(int(ops.fn("mca_mean_pool_scratch_floats")(B, R)), device=dev)
+    call("mca_mean_pool_fwd", P(x), P(pad8), P(ps), B, N, R, 512, P(pooled), P(cnt), P(scratch), stream())
+    xr = x.float().requires_grad_(True)
+    want = torch.zeros(B, R, 512, device=dev)
+    rows = []
+    for b in range(B):
+        for r in range(R):
+            live = ~pad[b, starts[r]:starts[r + 1]]
+            seg = xr[b, starts[r]:starts[r + 1]][live]
+            rows.append(seg.mean(0) if seg.shape[0] else torch.zeros(512, device=dev))
+            assert float(cnt[b, r]) == float(live.sum())
+    want = torch.stack(rows).view(B, R, 512)
+    assert rel_err(pooled, want) < 1e-5
+    assert float(pooled[0, 0].abs().max()) == 0.0
+    dp = torch.randn(B, R, 512, device=dev)
+    want.backward(dp)
+    dx = torch.full((B, N, 512), 7.0, device=dev)
+    call("mca_mean_pool_bwd", P(dp), P(pad8), P(tok_pass), P(cnt), B, N, R, 512, P(dx), stream())
+    assert rel_err(dx, xr.grad) < 1e-5
+    assert float(dx[pad].abs().max()) == 0.0

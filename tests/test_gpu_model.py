@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from mca_paper_b200 import config as C, synthetic as S
-from mca_paper_b200.model import MCA
+from mca_paper_b200.model import EAO, MCA
 from mca_paper_b200.trainer import Trainer
 from oracle import mca_oracle as O
 from tests import helpers as H
@@ -98,6 +98,66 @@ def test_gradients_match_oracle_well_conditioned(kind, kwargs, variant):
     errs.sort(reverse=True)
     assert errs[0][0] < 5e-2, errs[:5]
     assert errs[len(errs) // 2][0] < 1.5e-2, errs[len(errs) // 2]
+
+
+def test_eao_gradients_match_oracle_well_conditioned():
+    """EAO baseline (model.py:481-596; 4 single + 6 pair passes run as one block-diagonal packed sequence, mean pooling,
+    26 losses): every parameter gradient against oracle autograd of the pass-by-pass restatement, with a small final
+    norm gain and T = 1 so that bf16 rounding is not amplified by a saturated softmax.  Ragged lengths and absent
+    modalities: a pass whose modalities are all absent pools to zeros and is masked out of every loss."""
+    cfg = C.tiny_config("cmu", fcl=True, bimodal=True, non_fusion_fcl=True, eao=True)
+    kw = C.get_model_config(cfg)
+    torch.manual_seed(0)
+    model = EAO(**kw)
+    with torch.no_grad():
+        model.norm.gamma.mul_(0.02)
+        model.loss.loss_fn.logit_scale.fill_(0.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = S.make_batch(cfg, seed=1, variant="dropout_ragged")
+    names = [k for k, _ in model.named_parameters()]
+    params = {k: sd[k].clone().requires_grad_(True) for k in names}
+    sd2 = dict(sd)
+    sd2.update(params)
+    ref = O.eao_forward(sd2, kw, batch)
+    ref["loss"].backward()
+    model = model.to(dev)
+    out = model(S.batch_to(batch, dev))
+    out["loss"].backward()
+    assert list(out.keys()) == list(ref.keys())
+    for k in list(out.keys())[:10]:                                            # 4 modality + 6 pair embeddings
+        assert H.rel_err(out[k], ref[k]) < BF16_TOL, k
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-3 * abs(ref["loss"].item())
+    for k, v in ref["losses"].items():
+        assert bool(torch.isnan(v)) == bool(torch.isnan(out["losses"][k])), k
+    errs = []
+    for k, p in model.named_parameters():
+        g = params[k].grad
+        if g is None or float(g.abs().max()) == 0.0:
+            continue
+        errs.append((H.rel_err(p.grad, g), k))
+    errs.sort(reverse=True)
+    assert errs[0][0] < 5e-2, errs[:5]
+    assert errs[len(errs) // 2][0] < 1.5e-2, errs[len(errs) // 2]
+
+
+def test_eao_fused_trainer_steps():
+    """The fused (CUDA-graph) trainer drives EAO like MCA: gradients equal the autograd path's, the loss goes down."""
+    cfg = C.tiny_config("cmu", fcl=True, bimodal=True, non_fusion_fcl=True, eao=True)
+    kw = C.get_model_config(cfg)
+    torch.manual_seed(0)
+    model = EAO(**kw).to(dev)
+    batch = S.make_batch(cfg, seed=1, variant="dropout_ragged")
+    out = model(S.batch_to(batch, dev))
+    out["loss"].backward()
+    g_auto = torch.cat([p.grad.flatten() for p in model.parameters()])
+    tr = Trainer(model, lr=1e-4, clip=2.0, use_graphs=True)
+    tr.stage(batch)
+    tr.eng.pack_weights()
+    tr._seg_forward(), tr._seg_loss(), tr._seg_backward()
+    g_fused = torch.cat([tr.eng.gview(k).flatten() for k, _ in model.named_parameters()])
+    assert H.rel_err(g_fused, g_auto) < 1e-3
+    losses = [float(tr.step(batch)[0]) for _ in range(10)]
+    assert all(math.isfinite(x) for x in losses) and losses[-1] < losses[0]
 
 
 def test_no_loss_and_eval_mode_outputs():

@@ -164,3 +164,82 @@ def test_optimizer_shards_partition_the_flat_buffer():
                 assert off == min(pos, n_flat)
                 pos = off + n
             assert pos == n_flat
+
+
+def _eao_plan(kw):
+    from mca_paper_b200.plan import EAOPlan
+    return EAOPlan(kw["encoder_configs"], kw["fusion_combos"], kw["fcl"], kw["zorro"], kw["no_fusion"],
+                   kw["bimodal_contrastive"], kw["non_fusion_fcl"])
+
+
+def test_eao_plan_stacks_passes_block_diagonally():
+    """EAO (model.py:583-587): one pass per modality, one per combination, each over the packed tokens of its
+    modalities with key padding only.  The plan lays the passes back to back: check the layout against the oracle's
+    pass list, the bitmask form against the dense block-diagonal mask, the tile schedule against the dense mask, and
+    the loss plan against the oracle's (= MCAPretrainingLoss with no_fusion)."""
+    kw = C.get_model_config(C.tiny_config("cmu", fcl=True, bimodal=True, non_fusion_fcl=True, eao=True))
+    p = _eao_plan(kw)
+    passes = O.eao_passes(kw)
+    assert p.passes == passes and p.R == len(passes) == 10
+    lengths = [e["max_tokens"] for e in kw["encoder_configs"].values()]
+    pid, src = [], []                                    # per stacked token: its pass and its source token
+    for pi, members in enumerate(passes):
+        for m in members:
+            pid += [pi] * lengths[m]
+            src += list(range(sum(lengths[:m]), sum(lengths[:m]) + lengths[m]))
+    pid, src = np.asarray(pid), np.asarray(src)
+    assert p.N == len(pid) and np.array_equal(p.tok_pass, pid)
+    assert np.array_equal(np.asarray(p.pass_start), np.concatenate([[0], np.cumsum(np.bincount(pid))]))
+    assert np.array_equal(src[:p.n_tok], np.arange(p.n_tok))               # the single passes ARE the encoder outputs
+    got = np.arange(p.N)
+    for dst, s, L in p.replicas:
+        got[dst:dst + L] = np.arange(s, s + L)
+    assert np.array_equal(got, src)                                         # every later block replicates a modality
+    assert [sum(lengths[:m]) for m in p.mask_src] == [int(src[o]) for o in p.block_offsets]
+    dense = pid[:, None] != pid[None, :]
+    assert np.array_equal(p.attn_mask, dense)
+    allowed = ((p.rowbits[:, None] >> p.keygrp[None, :].astype(np.uint32)) & 1).astype(bool)
+    assert np.array_equal(allowed, ~dense)
+    cover = np.zeros((p.N, p.N), dtype=bool)
+    for qs, ql, off, cnt in p.q_tiles:
+        for ki, flag in p.kt_list[off:off + cnt]:
+            ks, kl = p.tiles[ki]
+            assert flag == 0 and not dense[qs:qs + ql, ks:ks + kl].any()    # block structure: every listed tile is full
+            cover[qs:qs + ql, ks:ks + kl] = True
+    assert np.array_equal(cover, ~dense) and p.allowed_pairs == int((~dense).sum())
+    plan, row = O.loss_plan(kw)
+    assert [x["name"] for x in plan] == p.loss_names and len(plan) == 26
+    for x, y in zip(plan, p.loss_plan):
+        assert (x["a"], x["b"]) == (y["a"], y["b"])
+        assert sum(1 << i for i in x["all"]) == y["all"] and sum(1 << i for i in x["any"]) == y["any"]
+    assert [k for k, _ in p.output_rows] == list(kw["encoder_configs"].keys()) + list(p.combos)
+
+
+def test_eao_plan_full_size_and_limits():
+    """CMU_config1_EAO (configs/CMU_config1_EAO.yaml): 4 + 6 passes, 9800 stacked tokens per sample, 16 key groups."""
+    cfg = C.named_config("CMU_config1")
+    enc = cfg["encoder_configs"]
+    from mca_paper_b200.plan import EAOPlan
+    p = EAOPlan(enc, [2], True, False, True, True, True)
+    assert (p.N, p.R, p.n_groups, p.n_tok) == (9800, 10, 16, 2450)
+    assert p.allowed_pairs == sum(int(n) ** 2 for n in np.diff(p.pass_start))
+    with pytest.raises(NotImplementedError):
+        EAOPlan(enc, [2], True, False, False, True, True)          # a fusion row EAO never pools (model.py:190)
+    assert EAOPlan(enc, [4, 3, 2], True, False, True, True, True).n_groups == 32     # 4 + 4 + 12 + 12 blocks: the limit
+    enc5 = dict(enc, extra={"type": "EmbeddedSequenceEncoder", "input_size": 16, "max_tokens": 40})
+    with pytest.raises(AssertionError):
+        EAOPlan(enc5, [3, 2], True, False, True, True, True)       # 5 + 30 + 20 blocks > 32 key groups
+
+
+def test_eao_model_schema_and_cpu_refusal():
+    from mca_paper_b200.model import EAO
+    kw = C.get_model_config(C.tiny_config("cmu", fcl=True, bimodal=True, non_fusion_fcl=True, eao=True))
+    m = EAO(**kw)
+    keys = list(m.state_dict().keys())
+    assert "return_tokens" not in keys and "fusion_tokens" not in keys and not any(k.startswith("attn_pool") for k in keys)
+    assert "token_types" in keys and m.state_dict()["token_types"].shape == (285,)
+    with pytest.raises(NotImplementedError):
+        EAO(**dict(kw, mean_pool=False))
+    batch = S.make_batch(C.tiny_config("cmu", eao=True), seed=1, variant="full")
+    with pytest.raises(_lib.MCAKernelError):
+        m(batch)

@@ -20,7 +20,7 @@ def test_oracle_matches_golden(case):
     params = {k: sd[k].clone().requires_grad_(True) for k in names}
     sd2 = dict(sd)
     sd2.update(params)
-    out = O.mca_forward(sd2, kw, batch)
+    out = H.oracle_forward(kw)(sd2, kw, batch)
     assert [H.key_to_str(k) for k in out.keys()] == gold["output_keys"]          # Q17: keys and order
     assert list(out["losses"].keys()) == list(gold["losses"].keys())
     for k, v in out.items():
@@ -66,15 +66,15 @@ def test_static_tables_match_reference_hashes():
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="live reference only exists in the build container")
-@pytest.mark.parametrize("case", ["tiny_cmu_fcl_ragged", "tiny_tcga_all_losses"])
+@pytest.mark.parametrize("case", ["tiny_cmu_fcl_ragged", "tiny_tcga_all_losses", "tiny_cmu_eao"])
 def test_oracle_matches_live_reference(case):
     cfg, kw, model, sd, batch = H.build_case(case)
-    ref = ref_shim.build_reference_model(kw, state_dict={k: v.clone() for k, v in sd.items()})
+    ref = ref_shim.build_reference_model(kw, state_dict={k: v.clone() for k, v in sd.items()})   # strict: same schema
     t = O.static_tables(kw)
-    for name in ("token_types", "attn_mask", "pool_mask"):
+    for name in (("token_types",) if kw.get("eao") else ("token_types", "attn_mask", "pool_mask")):
         assert torch.equal(t[name], getattr(ref, name)), name
     out_ref = ref_shim.reference_forward(ref, batch)
-    out = O.mca_forward({k: v.clone() for k, v in sd.items()}, kw, batch)
+    out = H.oracle_forward(kw)({k: v.clone() for k, v in sd.items()}, kw, batch)
     assert list(out.keys()) == list(out_ref.keys())
     torch.testing.assert_close(out["loss"], out_ref["loss"].detach(), rtol=1e-5, atol=1e-5)
 
