@@ -100,10 +100,11 @@ def cpu_training_step_fn(cfg_name: str, batch_size: int):
     cfg = C.named_config(cfg_name)
     cfg["batch_size"] = batch_size
     kw = C.get_model_config(cfg)
-    from mca_paper_b200.model import MCA
+    from mca_paper_b200.model import EAO, MCA
 
     torch.manual_seed(43)
-    model = MCA(**kw)  # parameter container only (CPU); arithmetic below is the oracle's
+    model = (EAO if kw.get("eao") else MCA)(**kw)  # parameter container only (CPU); arithmetic below is the oracle's
+    oracle_forward = O.eao_forward if kw.get("eao") else O.mca_forward
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     names = [k for k, _ in model.named_parameters()]
     params = [sd[k].requires_grad_(True) for k in names]
@@ -117,7 +118,7 @@ def cpu_training_step_fn(cfg_name: str, batch_size: int):
         state["step"] += 1
         for p in params:
             p.grad = None
-        out = O.mca_forward(sd, kw, batch, tables=tables)
+        out = oracle_forward(sd, kw, batch, tables=tables)
         out["loss"].backward()
         with torch.no_grad():
             O.clip_adamw_step([p for p in params], [p.grad if p.grad is not None else torch.zeros_like(p) for p in params],
@@ -284,13 +285,13 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
 
     from mca_paper_b200 import config as C, ops, synthetic as S
-    from mca_paper_b200.model import MCA
+    from mca_paper_b200.model import EAO, MCA
     from mca_paper_b200.trainer import Trainer
 
     cfg = C.named_config(args.config)
     kw = C.get_model_config(cfg)
     torch.manual_seed(int(cfg["seed"]))
-    model = MCA(**kw).to(dev)
+    model = (EAO if kw.get("eao") else MCA)(**kw).to(dev)   # train_accel_gpu.py:47-52
     trainer = Trainer(model, lr=float(cfg["lr"]), clip=float(cfg["clip"]), schedule="cosine",
                       warmup_steps=int(cfg["num_warmup_steps"]), total_steps=100000, use_graphs=not args.no_graphs)
     eng = trainer.eng
@@ -408,7 +409,8 @@ def main():
             dur = per_kernel[top]["us_avg"] * 1e-6
             ach = f / dur / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(tname),
+                    "frac": ach / peaks["bf16_tflops_sustained"],
+                    "traffic": ncu_traffic(tname) if args.config == "CMU_config1" else None,  # captured on that workload
                     "algorithmic_flops_per_launch": f, "avg_launch_us": per_kernel[top]["us_avg"],
                     "launches_per_step": per_kernel[top]["launches_per_step"],
                     "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
@@ -446,9 +448,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.config} MCA training step, B=8 per GPU (COVAREP 1500x74, FACET 450x35, OpenFace 450x713, "
-                                   f"GloVe 50x300, 88 fusion tokens -> N=2538, d=512, 5 layers, {eng.plan.n_pairs} InfoNCE pairs), "
-                                   f"variant={args.variant}",
+            "config": {"workload": (f"{args.config} EAO training step, B=8 per GPU ({eng.plan.n_mod} modalities, {eng.R} passes "
+                                    f"stacked block-diagonally -> N={eng.N} tokens per sample, d=512, {eng.depth} layers, mean "
+                                    f"pooling, {eng.plan.n_pairs} InfoNCE pairs), variant={args.variant}") if eng.eao else
+                                   (f"{args.config} MCA training step, B=8 per GPU (COVAREP 1500x74, FACET 450x35, OpenFace 450x713, "
+                                    f"GloVe 50x300, 88 fusion tokens -> N=2538, d=512, 5 layers, {eng.plan.n_pairs} InfoNCE pairs), "
+                                    f"variant={args.variant}"),
                        "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graphs": not args.no_graphs,
                        "dp_exchange": ("none" if world == 1 else ("peer memory (push/pull kernels + flag barriers, one graph)"
                                                                  if eng._p2p is not None else "nccl")),

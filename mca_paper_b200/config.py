@@ -139,6 +139,10 @@ NAMED_CONFIGS: Dict[str, Dict[str, Any]] = {
         },
         bimodal_contrastive=True, non_fusion_fcl=True, fcl=True, zorro=False),
 }
+# the "everything at once" baseline (configs/CMU_config1_EAO.yaml:1-28): pair passes, mean pooling, no fusion tokens
+NAMED_CONFIGS["CMU_config1_EAO"] = dict(NAMED_CONFIGS["CMU_config1"], bimodal_contrastive=True, non_fusion_fcl=True,
+                                        fcl=True, fcl_root=[0, 1], fusion_combos=[2], zorro=False, eao=True,
+                                        no_fusion=True, mean_pool=True)
 # infer_accel_gpu.py's model (configs/CMU_config1_z_12i.yaml) has the CMU_config1_z geometry
 NAMED_CONFIGS["CMU_config1_z_12i"] = dict(NAMED_CONFIGS["CMU_config1_z"])
 

@@ -34,7 +34,7 @@ constexpr int AB_TILE = AB_T * AB_DH * 2;  // 16 KB bf16 [128, 64]
 constexpr int AB_DS = AB_T * AB_T * 2;     // 32 KB bf16 dS tile, stored [key][query] in two 64-query halves
 constexpr int AB_DQ = AB_T * AB_DH * 4;    // 32 KB fp32 [128, 64]
 constexpr int AB_QSTAGES = 3;
-constexpr int AB_MAX_ITERS = 64;  // query tiles attending one key tile
+constexpr int AB_MAX_ITERS = 128;  // upper bound of query tiles attending one key tile (the launcher checks the total)
 // sK, sV, 3x(sQ, sdO), sdS (half 0 double buffered, half 1 single), sdQ, extra k-step operands; barriers are static
 // extra k-step operands (K-major, no swizzle: 8-row x 16-byte core matrices).  Only the first 8-element k chunk of a
 // row carries data; the second chunk of EVERY operand is the same all-zero block (the descriptor's leading-dimension
