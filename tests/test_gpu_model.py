@@ -100,12 +100,13 @@ def test_gradients_match_oracle_well_conditioned(kind, kwargs, variant):
     assert errs[len(errs) // 2][0] < 1.5e-2, errs[len(errs) // 2]
 
 
-def test_eao_gradients_match_oracle_well_conditioned():
+@pytest.mark.parametrize("kind,variant", [("cmu", "dropout_ragged"), ("tcga", "tcga")])
+def test_eao_gradients_match_oracle_well_conditioned(kind, variant):
     """EAO baseline (model.py:481-596; 4 single + 6 pair passes run as one block-diagonal packed sequence, mean pooling,
     26 losses): every parameter gradient against oracle autograd of the pass-by-pass restatement, with a small final
     norm gain and T = 1 so that bf16 rounding is not amplified by a saturated softmax.  Ragged lengths and absent
     modalities: a pass whose modalities are all absent pools to zeros and is masked out of every loss."""
-    cfg = C.tiny_config("cmu", fcl=True, bimodal=True, non_fusion_fcl=True, eao=True)
+    cfg = C.tiny_config(kind, fcl=True, bimodal=True, non_fusion_fcl=True, eao=True)
     kw = C.get_model_config(cfg)
     torch.manual_seed(0)
     model = EAO(**kw)
@@ -113,7 +114,7 @@ def test_eao_gradients_match_oracle_well_conditioned():
         model.norm.gamma.mul_(0.02)
         model.loss.loss_fn.logit_scale.fill_(0.0)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    batch = S.make_batch(cfg, seed=1, variant="dropout_ragged")
+    batch = S.make_batch(cfg, seed=1, variant=variant)
     names = [k for k, _ in model.named_parameters()]
     params = {k: sd[k].clone().requires_grad_(True) for k in names}
     sd2 = dict(sd)
@@ -138,6 +139,14 @@ def test_eao_gradients_match_oracle_well_conditioned():
     errs.sort(reverse=True)
     assert errs[0][0] < 5e-2, errs[:5]
     assert errs[len(errs) // 2][0] < 1.5e-2, errs[len(errs) // 2]
+    # inference call of infer_accel_gpu.py:106 (eval, no_grad, no_loss): embeddings only, same keys as the reference
+    model.eval()
+    with torch.no_grad():
+        emb = model(S.batch_to(batch, dev), no_loss=True)
+    ref_emb = O.eao_forward(sd, kw, batch, no_loss=True)
+    assert list(emb.keys()) == list(ref_emb.keys())
+    for k in list(emb.keys())[:-1]:
+        assert H.rel_err(emb[k], ref_emb[k]) < BF16_TOL, k
 
 
 def test_eao_fused_trainer_steps():
