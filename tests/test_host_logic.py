@@ -243,3 +243,64 @@ def test_eao_model_schema_and_cpu_refusal():
     batch = S.make_batch(C.tiny_config("cmu", eao=True), seed=1, variant="full")
     with pytest.raises(_lib.MCAKernelError):
         m(batch)
+
+
+def _random_geometry_strategy():
+    from hypothesis import strategies as st
+    return st.tuples(
+        st.lists(st.integers(min_value=1, max_value=300), min_size=2, max_size=4),          # modality lengths
+        st.sampled_from([[2], [3, 2], [4, 3, 2], [2, 3]]),                                  # fusion_combos powers
+        st.integers(min_value=1, max_value=9),                                              # fusion tokens per combination
+        st.sampled_from(["mca_fcl", "mca", "mma", "bimodal_fcl", "eao"]))
+
+
+def test_plans_match_oracle_tables_on_random_geometries():
+    """Property test over random modality counts / lengths (tiles of 128 that never straddle a block, ragged tails),
+    combination sets and model families: the plan's bitmask form, dense masks, tile schedule and loss plan agree with
+    the oracle's dense restatement of model.py:383-446 / 151-220 (EAO: the block-diagonal pass layout)."""
+    from hypothesis import HealthCheck, given, settings
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(_random_geometry_strategy())
+    def check(geo):
+        lengths, powers, nsub, family = geo
+        n = len(lengths)
+        powers = [k for k in powers if k <= n] or [2]
+        enc = {f"m{i}": {"type": "EmbeddedSequenceEncoder", "input_size": 8, "max_tokens": L} for i, L in enumerate(lengths)}
+        n_combos = len(O.modality_combos(n, powers))
+        kw = dict(encoder_configs=enc, num_fusion_tokens=nsub * n_combos, fusion_combos=powers, fcl=family in ("mca_fcl", "bimodal_fcl", "eao"),
+                  zorro=family == "mma", no_fusion=family == "eao", bimodal_contrastive=family in ("bimodal_fcl", "eao"),
+                  non_fusion_fcl=family in ("bimodal_fcl", "eao"), eao=family == "eao", batch_size=2, depth=1, heads=8)
+        if family == "eao":
+            if n + sum(len(c) for c in O.modality_combos(n, powers)) > 32:
+                return
+            p = _eao_plan(kw)
+            pid = np.concatenate([np.full(sum(lengths[m] for m in members), pi) for pi, members in enumerate(O.eao_passes(kw))])
+            dense = pid[:, None] != pid[None, :]
+        else:
+            p = make_plan(kw)
+            t = O.static_tables(kw)
+            dense = t["attn_mask"].numpy()
+            assert np.array_equal(p.pool_mask, t["pool_mask"].numpy()) and np.array_equal(p.token_types, t["token_types"].numpy())
+        assert np.array_equal(p.attn_mask, dense)
+        rec = ~(((p.rowbits[:, None] >> p.keygrp[None, :].astype(np.uint32)) & 1).astype(bool))
+        assert np.array_equal(rec, dense)
+        covered = np.zeros_like(dense)
+        for qs, ql, off, cnt in p.q_tiles:
+            for ki, flag in p.kt_list[off:off + cnt]:
+                ks, kl = p.tiles[ki]
+                blk = ~dense[qs:qs + ql, ks:ks + kl]
+                assert blk.any() and (flag == 0) == bool(blk.all())
+                covered[qs:qs + ql, ks:ks + kl] = True
+        assert not (~dense & ~covered).any()
+        assert p.tiles[:, 1].max() <= 128 and (p.tiles[:, 0] + p.tiles[:, 1])[-1] == p.N
+        fwd = {(qi, int(ki)) for qi, (_, _, off, cnt) in enumerate(p.q_tiles) for ki, _ in p.kt_list[off:off + cnt]}
+        bwd = {(int(qi), ki) for ki, (_, _, off, cnt) in enumerate(p.k_tiles_q) for qi, _ in p.qt_list[off:off + cnt]}
+        assert fwd == bwd
+        plan, _ = O.loss_plan(kw)
+        assert [x["name"] for x in plan] == p.loss_names
+        for x, y in zip(plan, p.loss_plan):
+            assert (x["a"], x["b"]) == (y["a"], y["b"])
+            assert sum(1 << i for i in x["all"]) == y["all"] and sum(1 << i for i in x["any"]) == y["any"]
+
+    check()
