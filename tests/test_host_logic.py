@@ -304,3 +304,32 @@ def test_plans_match_oracle_tables_on_random_geometries():
             assert sum(1 << i for i in x["all"]) == y["all"] and sum(1 << i for i in x["any"]) == y["any"]
 
     check()
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every entry point's ctypes argument list (mca_paper_b200/ops.py) against its declaration in include/mca_b200.h:
+    same arity, and the same class per argument (pointer / int / long long / float / unsigned long long) — a drifted
+    binding would pass garbage to a kernel instead of failing."""
+    header = open(os.path.join(ROOT, "include", "mca_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    decls = dict(re.findall(r"^int (mca_\w+)\((.*?)\);", header, flags=re.M | re.S))
+    assert set(decls) == set(ops._SIGS)
+
+    def cls(param: str):
+        p = " ".join(param.split())
+        if p == "void":
+            return None
+        if "*" in p:
+            return ctypes.c_void_p
+        base = " ".join(p.split(" ")[:-1]).replace("const ", "")
+        return {"int": ctypes.c_int32, "long long": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
+                "unsigned long long": ctypes.c_uint64, "unsigned int": ctypes.c_uint32}[base]
+
+    for name, params in decls.items():
+        want = [c for c in (cls(x) for x in params.split(",")) if c is not None]
+        got = list(ops._SIGS[name])
+        assert len(want) == len(got), (name, len(want), len(got))
+        for i, (w, g) in enumerate(zip(want, got)):
+            is_f = lambda c: c in (ctypes.c_float, ctypes.c_double)
+            same = ctypes.sizeof(w) == ctypes.sizeof(g) and (w is ctypes.c_void_p) == (g is ctypes.c_void_p) and is_f(w) == is_f(g)
+            assert same, (name, i, w, g)
