@@ -34,7 +34,8 @@ def scheduler_state_dict(eng, step: int) -> Dict:
     has been advanced step * stride times (accelerate steps it once per process)."""
     stride = max(1, int(eng.adamw_cfg.sched_stride))
     return {"base_lrs": [float(eng.adamw_cfg.lr)], "last_epoch": step * stride, "_step_count": step * stride + 1,
-            "_get_lr_called_within_step": False, "_last_lr": [eng.lr_at(step + 1)], "lr_lambdas": [{}]}
+            "_is_initial": False, "_get_lr_called_within_step": False, "_last_lr": [eng.lr_at(step + 1)],
+            "lr_lambdas": [{}]}
 
 
 def model_state_dict(model) -> Dict[str, torch.Tensor]:
@@ -116,7 +117,7 @@ def load_state(trainer, input_dir: str, strict: bool = True) -> int:
         step = max(steps) if steps else 0
     p = os.path.join(input_dir, SCHEDULER_NAME)
     if os.path.exists(p):
-        sch = torch.load(p, map_location="cpu", weights_only=False)
+        sch = torch.load(p, map_location="cpu", weights_only=True)   # a plain dict of numbers / lists (no pickled code)
         stride = max(1, int(eng.adamw_cfg.sched_stride))
         if int(sch.get("last_epoch", step * stride)) != step * stride:
             raise ValueError(f"scheduler.bin is at scheduler step {sch.get('last_epoch')} but the optimiser state is at "

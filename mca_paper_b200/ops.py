@@ -90,6 +90,9 @@ def fn(name: str):
 
 
 def P(t):
+    """Device address of a tensor for a C-ABI call (None -> NULL).  The caller keeps `t` referenced until `call()` has
+    returned: `P(torch.empty(...))` inside an argument list frees the temporary at once and the caching allocator may
+    hand the same block to the next temporary of that list (two "distinct" scratch buffers then alias)."""
     if t is None:
         return None
     return t.data_ptr()
