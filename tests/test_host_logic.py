@@ -333,3 +333,22 @@ def test_ctypes_signatures_match_the_header():
             is_f = lambda c: c in (ctypes.c_float, ctypes.c_double)
             same = ctypes.sizeof(w) == ctypes.sizeof(g) and (w is ctypes.c_void_p) == (g is ctypes.c_void_p) and is_f(w) == is_f(g)
             assert same, (name, i, w, g)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/configs"), reason="reference YAMLs only exist in the build container")
+@pytest.mark.parametrize("name", ["CMU_config1", "CMU_config1_z", "CMU_config1_d40", "TCGA_config1", "CMU_config1_EAO",
+                                  "CMU_config1_z_12i"])
+def test_named_configs_equal_the_reference_yaml(name):
+    """The in-repo copies of the benchmark configurations give the model the same kwargs as the reference's YAML run
+    through its own defaults (utils/config.py:9-57 defaults, :96-117 get_model_config)."""
+    mine = C.get_model_config(C.named_config(name))
+    theirs = C.get_model_config(C.training_config(f"/root/reference/configs/{name}.yaml"))
+    assert set(mine) == set(theirs)
+    for k in mine:
+        a, b = mine[k], theirs[k]
+        if k == "encoder_configs":
+            assert list(a.keys()) == list(b.keys())
+            for m in a:
+                assert dict(a[m]) == dict(b[m]), (m, a[m], b[m])
+        else:
+            assert (list(a) if isinstance(a, (list, tuple)) else a) == (list(b) if isinstance(b, (list, tuple)) else b), k

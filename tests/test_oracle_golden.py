@@ -90,3 +90,28 @@ def test_multi_rank_emulation_rows_and_labels():
         a, b = outs[0]["losses"][k], outs[1]["losses"][k]
         assert (torch.isnan(a) and torch.isnan(b)) or torch.allclose(a, b, rtol=1e-5, atol=1e-6)
     assert not torch.allclose(outs[0]["loss"], single["loss"])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="live reference only exists in the build container")
+@pytest.mark.parametrize("kind,variant", [("tcga", "tcga"), ("mixed", "dropout_ragged")])
+def test_eao_oracle_matches_live_reference_other_encoders(kind, variant):
+    """EAO restatement (oracle eao_forward, model.py:567-596) against the live reference EAO on the TabularEncoder and
+    the Sequence / SparseTabular / Patch encoder geometries (the committed fixture covers EmbeddedSequenceEncoder)."""
+    from mca_paper_b200 import config as C, synthetic as S
+    from mca_paper_b200.model import EAO
+    cfg = C.tiny_config(kind, fcl=True, bimodal=True, non_fusion_fcl=True, eao=True)
+    kw = C.get_model_config(cfg)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in EAO(**kw).state_dict().items()}
+    batch = S.make_batch(cfg, seed=2, variant=variant)
+    ref = ref_shim.build_reference_model(kw, state_dict={k: v.clone() for k, v in sd.items()})
+    ref.eval()  # PatchEncoder's nn.Dropout off (the oracle restates the deterministic part)
+    out_ref = ref_shim.reference_forward(ref, batch)
+    out = O.eao_forward({k: v.clone() for k, v in sd.items()}, kw, batch)
+    assert list(out.keys()) == list(out_ref.keys()) and list(out["losses"]) == list(out_ref["losses"])
+    for k, v in out_ref["losses"].items():
+        if torch.isnan(v):
+            assert torch.isnan(out["losses"][k]), k
+        else:
+            torch.testing.assert_close(out["losses"][k], v.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out["loss"], out_ref["loss"].detach(), rtol=1e-5, atol=1e-5)
