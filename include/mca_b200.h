@@ -70,7 +70,7 @@ typedef struct {
 
 typedef struct {
   float lr, beta1, beta2, eps, weight_decay, max_norm; /* max_norm <= 0: no clipping */
-  int lr_mode;                                         /* 0 constant, 1 cosine with linear warm-up */
+  int lr_mode;                                         /* 0 constant, 1 cosine, 2 constant_with_warmup, 3 linear (1-3: linear warm-up) */
   long long warmup_steps, total_steps;
   long long sched_stride;                              /* scheduler.step() calls per optimiser step: accelerate's
                                                           prepared scheduler advances num_processes times per step

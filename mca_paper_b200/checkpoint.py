@@ -15,6 +15,7 @@ moments of its shard only: `save_state` gathers them (every rank must call it), 
 """
 from __future__ import annotations
 
+import json
 import os
 import pickle
 import random
@@ -27,6 +28,7 @@ MODEL_NAME_BIN = "pytorch_model.bin"
 OPTIMIZER_NAME = "optimizer.bin"
 SCHEDULER_NAME = "scheduler.bin"
 RNG_NAME = "random_states_{rank}.pkl"
+STATE_NAME = "mca_b200_state_{rank}.json"   # plain-data side file: optimiser step + dropout-stream position
 
 
 def scheduler_state_dict(eng, step: int) -> Dict:
@@ -81,6 +83,7 @@ def save_state(trainer, output_dir: str, safe_serialization: bool = True) -> Opt
     """accelerator.save_state(output_dir) for the fused trainer.  Collective under data parallelism (the optimiser
     shards are gathered); only rank 0 writes the model / optimiser / scheduler files."""
     eng = trainer.eng
+    eng.check_p2p()  # never checkpoint a run in which a peer missed an exchange barrier
     opt = trainer.optimizer_state_dict()  # gathers the shards: every rank takes part
     step = int(float(opt["state"][0]["step"])) if opt["state"] else 0
     os.makedirs(output_dir, exist_ok=True)
@@ -93,8 +96,12 @@ def save_state(trainer, output_dir: str, safe_serialization: bool = True) -> Opt
         pass
     if torch.cuda.is_available():
         rng["torch_cuda_manual_seed"] = torch.cuda.get_rng_state_all()
+    # accelerate's per-rank RNG file, written for layout compatibility only: load_state never unpickles it
     with open(os.path.join(output_dir, RNG_NAME.format(rank=eng.rank)), "wb") as f:
         pickle.dump(rng, f)
+    # what THIS trainer needs back on resume, as plain JSON (no code execution on load)
+    with open(os.path.join(output_dir, STATE_NAME.format(rank=eng.rank)), "w") as f:
+        json.dump({"step": step, "drop_ctr": rng["drop_ctr"]}, f)
     if eng.rank != 0:
         return None
     save_model(trainer.model, output_dir, safe_serialization)
@@ -123,10 +130,12 @@ def load_state(trainer, input_dir: str, strict: bool = True) -> int:
             raise ValueError(f"scheduler.bin is at scheduler step {sch.get('last_epoch')} but the optimiser state is at "
                              f"step {step} x {stride} scheduler steps per step: resume with the world size (or "
                              "scheduler_stride) the checkpoint was written with")
-    p = os.path.join(input_dir, RNG_NAME.format(rank=eng.rank))
+    # the dropout-stream position comes from our own JSON side file; random_states_<rank>.pkl (accelerate's pickled
+    # host RNG states) is deliberately NOT read: unpickling a downloaded checkpoint would execute arbitrary code, and the
+    # fused step draws nothing from the host generators
+    p = os.path.join(input_dir, STATE_NAME.format(rank=eng.rank))
     if os.path.exists(p):
-        with open(p, "rb") as f:
-            rng = pickle.load(f)
-        if "drop_ctr" in rng:  # written by save_state above (accelerate's own files carry no such key)
-            eng.ws["drop_ctr"].fill_(int(rng["drop_ctr"]))
+        with open(p) as f:
+            st = json.load(f)
+        eng.ws["drop_ctr"].fill_(int(st.get("drop_ctr", 0)))
     return step

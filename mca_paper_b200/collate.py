@@ -12,8 +12,12 @@ GPU the reference's 8 CPU collator workers + a dense 14.8 MB/batch H2D (train_ac
     out = model(batch)
 
 Dropout: `dropout` entries of modality_config are applied per (sample, modality) with `torch.rand(1) < p` in the
-reference's order (sample-major, modality order of the sample dict), so a seeded run drops exactly what
-`batch_predrop` would; dropped modalities are never staged or copied.  Output tensors are reused between calls.
+reference's order (sample-major, modality order of the sample dict); dropped modalities are never staged or copied.
+Semantics differ from the reference in ONE documented way: `batch_predrop` (utils/dataset.py:59-69) draws the drops once,
+at dataset-construction time, so a sample keeps the same dropped modalities in every epoch; `apply_dropout=True` here
+redraws them at every call (fresh drops per epoch).  To reproduce the reference exactly, call `predrop(samples)` ONCE
+over the whole dataset under the run's seed (same RNG calls, same order) and collate the result with
+`apply_dropout=False`.  The device buffers handed out are reused every second call of the same collator.
 """
 from __future__ import annotations
 
@@ -49,17 +53,29 @@ class DeviceCollator:
 
     # ------------------------------------------------------------------------------------------------ staging
     def _staging(self, key, shape, dtype):
-        buf = self._buf.get(key)
-        if buf is None or buf[0].shape != torch.Size(shape) or buf[0].dtype != dtype:
-            buf = (torch.empty(shape, dtype=dtype, pin_memory=True), torch.empty(shape, dtype=dtype, device=self.device))
-            self._buf[key] = buf
-        return buf
+        """(pinned, device, event) for `key`.  Two pinned/device pairs per key are used alternately and each carries the
+        event recorded after its last H2D copy: the host only rewrites a pinned buffer whose copy has drained (the
+        collator never synchronises the device, so it can run several batches ahead of it)."""
+        entry = self._buf.get(key)
+        if entry is None or entry["bufs"][0][0].shape != torch.Size(shape) or entry["bufs"][0][0].dtype != dtype:
+            entry = {"bufs": [(torch.empty(shape, dtype=dtype, pin_memory=True),
+                               torch.empty(shape, dtype=dtype, device=self.device)) for _ in range(2)],
+                     "events": [None, None], "next": 0}
+            self._buf[key] = entry
+        i = entry["next"]
+        entry["next"] ^= 1
+        if entry["events"][i] is not None:
+            entry["events"][i].synchronize()
+        else:
+            entry["events"][i] = torch.cuda.Event()
+        pin, dev = entry["bufs"][i]
+        return pin, dev, entry["events"][i]
 
     def _stage_varlen(self, key, items: List[Optional[torch.Tensor]], max_rows: int, width: int, dtype):
         """Concatenate the items' rows (each truncated to max_rows) into pinned memory; returns (device rows, device
         offsets [B+1])."""
-        pin, dev = self._staging(key + ".rows", (self.B * max_rows, width) if width else (self.B * max_rows,), dtype)
-        opin, odev = self._staging(key + ".off", (self.B + 1,), torch.int32)
+        pin, dev, ev_rows = self._staging(key + ".rows", (self.B * max_rows, width) if width else (self.B * max_rows,), dtype)
+        opin, odev, ev_off = self._staging(key + ".off", (self.B + 1,), torch.int32)
         pos = 0
         opin[0] = 0
         for b, x in enumerate(items):
@@ -72,6 +88,8 @@ class DeviceCollator:
             dev[:pos].copy_(pin[:pos], non_blocking=True)
             self.h2d_bytes += pos * max(width, 1) * pin.element_size()
         odev.copy_(opin, non_blocking=True)
+        ev_rows.record()
+        ev_off.record()
         self.h2d_bytes += opin.numel() * 4
         return dev, odev
 

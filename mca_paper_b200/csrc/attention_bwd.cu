@@ -67,6 +67,9 @@ __device__ __forceinline__ void ab_bar_sync(int id, int n) { asm volatile("bar.s
 #ifdef MCA_TRACE
 // debug-only timeline (built with MCA_NVCC_EXTRA=-DMCA_TRACE): clock64 stamps of one CTA, read by mca_debug_read_trace
 __device__ long long g_trace[4 * 16 * 16 + 8];
+__device__ long long g_bcta[4096 * 4];  // (globaltimer start, end, smid, n_iter) of every CTA
+__device__ __forceinline__ long long gtimer_b() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int smid_b() { int s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
 #define TR(role, t, e) do { if (blockIdx.x == 5 && blockIdx.y == 3 && (t) < 16) g_trace[((role) * 16 + (t)) * 16 + (e)] = clock64(); } while (0)
 #define TRG(e) do { if (blockIdx.x == 5 && blockIdx.y == 3) g_trace[4 * 16 * 16 + (e)] = clock64(); } while (0)
 #else
@@ -115,6 +118,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const int cls = a.kt_class[static_cast<long long>(b) * a.n_kt + kt];
   const int n_iter = cls == 2 ? 0 : KT.kt_cnt;
   const int HD = a.H * AB_DH;
+#ifdef MCA_TRACE
+  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0 && cta_lin < 4096) { g_bcta[cta_lin * 4] = gtimer_b(); g_bcta[cta_lin * 4 + 2] = smid_b(); g_bcta[cta_lin * 4 + 3] = n_iter; }
+#endif
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -529,6 +536,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TRG(7);
+#ifdef MCA_TRACE
+  if (threadIdx.x == 0 && cta_lin < 4096) g_bcta[cta_lin * 4 + 1] = gtimer_b();
+#endif
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -638,5 +648,9 @@ extern "C" int mca_attn_bwd(const void* qkv, const void* out, const void* dout, 
 extern "C" int mca_debug_read_trace(long long* host_dst, int n) {
   cudaDeviceSynchronize();
   return cudaMemcpyFromSymbol(host_dst, mca::g_trace, sizeof(long long) * n) == cudaSuccess ? 0 : 3;
+}
+extern "C" int mca_debug_read_cta_bwd(long long* host_dst, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_dst, mca::g_bcta, sizeof(long long) * n) == cudaSuccess ? 0 : 3;
 }
 #endif

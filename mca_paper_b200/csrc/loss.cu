@@ -61,7 +61,7 @@ __device__ __forceinline__ bool row_selected(const LossArgs& a, const mca_loss_p
 // local b rows against every gathered a row.  The B local query rows are staged in shared memory once; each warp then
 // reads a gathered key row ONCE (coalesced float4) and dots it with all B queries, so the global traffic is GB rows per
 // CTA, not B*GB.  logits[i*GB + j] = T * q_i . k_j
-constexpr int LOSS_MAXB = 16;  // local batch rows held in registers by the backward
+constexpr int LOSS_MAXB = 32;  // local batch rows held in registers by the backward (configs/*_i.yaml use 32)
 
 __device__ void stage_and_logits(const LossArgs& a, const mca_loss_pair& p, int dir, float T, float* qs, float* lg) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -249,7 +249,8 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ w, float* __restrict__ dpo
 // ---- cross-GPU flag barrier over peer-mapped memory.  flags[g] (uint32[G], one array per rank, every rank can address
 // all of them): rank r publishes the barrier's epoch in slot r of EVERY rank's array (release, system scope) and waits
 // until every slot of its own array has reached the epoch (acquire).  The epoch is a device counter, so the same
-// captured graph can be replayed.  A peer that never arrives raises err_flag after ~10 s instead of hanging the GPU.
+// captured graph can be replayed.  A peer that never arrives is reported after ~10 s: err_flag (host-mapped) = 1 + its rank, then the kernel traps, so the
+// step fails loudly instead of hanging the GPU or running on with stale data.
 // Optional payload: one double of this rank (e.g. its partial gradient sum of squares) is stored into slot `rank` of
 // every rank's payload array before the flag is raised, so it is visible to whoever passes the barrier.
 __global__ void xgpu_barrier_kernel(uint32_t* const* __restrict__ flags_peers, int world, int rank,
@@ -273,8 +274,11 @@ __global__ void xgpu_barrier_kernel(uint32_t* const* __restrict__ flags_peers, i
     if (static_cast<int32_t>(v - e) >= 0) break;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     if (t1 - t0 > 10000000000ull) {
-      atomicExch(err_flag, 1);
-      break;
+      // A peer never arrived: record it where the host can still read it (err_flag is pinned host memory) and stop
+      // this GPU's step with a trap -- continuing would train on stale gathered rows / gradients / parameter shards.
+      *reinterpret_cast<volatile int*>(err_flag) = 1 + g;
+      __threadfence_system();
+      __trap();
     }
   }
 }
@@ -309,6 +313,7 @@ p2p_reduce_rows_kernel(const float* const* __restrict__ src_peers, long long off
 
 using namespace mca;
 
+constexpr int LOSS_MAX_SMEM = 200 * 1024;  // B = 32 local rows x (d = 512 + GB = 256 gathered columns) x 4 B = 96 KB
 static int loss_smem_bytes(int B, int GB, int d) { return (B * d + B * GB) * static_cast<int>(sizeof(float)); }
 
 extern "C" int mca_contrastive_allpairs_fwd(const float* pooled_all, const uint8_t* present,
@@ -318,12 +323,12 @@ extern "C" int mca_contrastive_allpairs_fwd(const float* pooled_all, const uint8
                                             void* stream_) {
   if (n_pairs <= 0 || B <= 0 || B > LOSS_MAXB || GB < B || (d % 4) != 0 || n_mod > MCA_MAX_MODALITIES) return MCA_ERR_SHAPE;
   const int smem = loss_smem_bytes(B, GB, d);
-  if (smem > 96 * 1024) return MCA_ERR_SHAPE;
+  if (smem > LOSS_MAX_SMEM) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOSS_MAX_SMEM);
+    cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOSS_MAX_SMEM);
     attr = true;
   }
   clamp_scale_kernel<<<1, 32, 0, stream>>>(logit_scale, scale_min, scale_max);
@@ -339,11 +344,11 @@ extern "C" int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8
                                             float* dpooled_all, float* dscale, void* stream_) {
   if (n_pairs <= 0 || B <= 0 || B > LOSS_MAXB || GB < B || (d % 4) != 0) return MCA_ERR_SHAPE;
   const int smem = loss_smem_bytes(B, GB, d);
-  if (smem > 96 * 1024) return MCA_ERR_SHAPE;
+  if (smem > LOSS_MAX_SMEM) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOSS_MAX_SMEM);
     attr = true;
   }
   LossArgs a{pooled_all, present, plan_dev, logit_scale, B, GB, R, d, n_mod, rank, n_pairs};

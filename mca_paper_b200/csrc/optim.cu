@@ -38,9 +38,14 @@ sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out)
 // state: [0] = step (as double, incremented here by block 0 AFTER use via the `commit` kernel), see below
 __device__ __forceinline__ float scheduled_lr(const mca_adamw_cfg& c, long long step /*1-based*/) {
   if (c.lr_mode == 0) return c.lr;
-  // transformers.get_cosine_schedule_with_warmup evaluated at (step-1): scheduler.step() follows optimizer.step()
+  // transformers.get_scheduler(name) evaluated at (step-1): scheduler.step() follows optimizer.step().
+  // 1 = "cosine", 2 = "constant_with_warmup", 3 = "linear" (all with linear warm-up over warmup_steps)
   const double cur = static_cast<double>(step - 1) * static_cast<double>(c.sched_stride > 1 ? c.sched_stride : 1);
   if (cur < c.warmup_steps) return c.lr * static_cast<float>(cur / fmax(1.0, static_cast<double>(c.warmup_steps)));
+  if (c.lr_mode == 2) return c.lr;
+  if (c.lr_mode == 3)
+    return c.lr * static_cast<float>(fmax(0.0, (static_cast<double>(c.total_steps) - cur) /
+                                                   fmax(1.0, static_cast<double>(c.total_steps - c.warmup_steps))));
   const double prog = (cur - c.warmup_steps) / fmax(1.0, static_cast<double>(c.total_steps - c.warmup_steps));
   return c.lr * static_cast<float>(fmax(0.0, 0.5 * (1.0 + cos(3.14159265358979323846 * prog))));
 }

@@ -25,6 +25,10 @@ DH = 64
 ALIGN = 64  # elements; keeps every parameter 256-byte aligned inside the flat buffers
 
 
+# transformers.get_scheduler names (train_accel_gpu.py:81-86 passes config.lr_scheduler_type) -> device lr_mode
+LR_MODES = {"constant": 0, "cosine": 1, "constant_with_warmup": 2, "linear": 3}
+
+
 def _round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -291,15 +295,23 @@ class Engine:
         if world > 1 and want:
             # rebuild the flat parameter / gradient buffers in symmetric memory (peers pull gradient shards from them and
             # push updated parameter shards into them), then the small exchange buffers
+            err = None
             try:
                 self._want_symm = True
                 self._flat_ptrs = None
                 self.ensure_flat()
                 self._setup_p2p()
             except Exception as exc:  # no P2P mapping between these GPUs / symmetric memory unavailable
+                err = exc
+            # the choice of exchange protocol is collective: one rank on the NCCL form while the others spin on peer
+            # flags would deadlock, so every rank learns whether ALL ranks succeeded before committing to either path
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device or "cuda")
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
                 import warnings
-                warnings.warn(f"peer-memory data parallelism unavailable ({type(exc).__name__}: {exc}); "
-                              "using the NCCL all_gather / reduce_scatter / all_reduce form")
+                why = f"{type(err).__name__}: {err}" if err is not None else "a peer rank could not set it up"
+                warnings.warn(f"peer-memory data parallelism unavailable ({why}); "
+                              "using the NCCL all_gather / reduce_scatter / all_reduce form on every rank")
                 self._want_symm, self._p2p, self._flat_ptrs = False, None, None
                 self.ensure_flat()
 
@@ -333,7 +345,8 @@ class Engine:
             "sumsq_local": torch.zeros(1, dtype=torch.float64, device=dev),
             "grad_peers": self._grad_peers, "param_peers": self._flat_peers,
             "epoch": torch.zeros(1, dtype=torch.int32, device=dev),
-            "err": torch.zeros(1, dtype=torch.int32, device=dev),
+            # pinned host memory (device-addressable under UVA): still readable after the barrier kernel trapped
+            "err": torch.zeros(1, dtype=torch.int32).pin_memory(),
         }
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)  # every rank's flags are zero before anybody raises one
@@ -356,9 +369,11 @@ class Engine:
         return ((n_flat + world - 1) // world + 3) // 4 * 4
 
     def check_p2p(self):
-        """Raises if a peer missed a flag barrier (read once per run, not per step)."""
-        if self._p2p is not None and int(self._p2p["err"].item()) != 0:
-            raise _lib.MCAKernelError("a peer GPU did not reach mca_xgpu_barrier within 10 s")
+        """Raises if a peer missed a flag barrier.  The flag lives in pinned host memory, so this is a plain host read
+        (no device synchronisation): Trainer calls it every step and checkpoint.save_state before writing."""
+        if self._p2p is not None and int(self._p2p["err"][0]) != 0:
+            raise _lib.MCAKernelError(f"rank {int(self._p2p['err'][0]) - 1} did not reach mca_xgpu_barrier within 10 s "
+                                      f"(seen by rank {self.rank}); the step was aborted")
 
     def _gather_buffers(self):
         if self._gather_ws is None:
@@ -769,8 +784,11 @@ class Engine:
         """scheduler_stride: scheduler.step() calls per optimiser step.  The reference prepares its scheduler with
         accelerate (train_accel_gpu.py:93), whose wrapper advances it num_processes times per step, so a run on G GPUs
         walks the cosine G times faster than its step count; pass G to reproduce that (Trainer does)."""
+        if schedule not in LR_MODES:
+            raise ValueError(f"unknown lr schedule {schedule!r}: expected one of {sorted(LR_MODES)} "
+                             "(transformers.get_scheduler names, train_accel_gpu.py:81-86)")
         self.adamw_cfg = ops.AdamWCfg(lr, betas[0], betas[1], eps, weight_decay, max_norm,
-                                      1 if schedule == "cosine" else 0, warmup_steps, total_steps,
+                                      LR_MODES[schedule], warmup_steps, total_steps,
                                       max(1, int(scheduler_stride)))
 
     def lr_at(self, step: int) -> float:
@@ -783,6 +801,10 @@ class Engine:
         cur = float(step - 1) * max(1, c.sched_stride)
         if cur < c.warmup_steps:
             return float(c.lr) * cur / max(1.0, float(c.warmup_steps))
+        if c.lr_mode == 2:
+            return float(c.lr)
+        if c.lr_mode == 3:
+            return float(c.lr) * max(0.0, (c.total_steps - cur) / max(1.0, float(c.total_steps - c.warmup_steps)))
         prog = (cur - c.warmup_steps) / max(1.0, float(c.total_steps - c.warmup_steps))
         return float(c.lr) * max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 

@@ -30,6 +30,16 @@ def adjusted_powerset(unique_tokens, powers=(2, 3)):
         yield tuple(sorted(c))
 
 
+MAX_BATCH_SIZE = 32  # LOSS_MAXB of csrc/loss.cu: local rows the all-pairs loss kernels keep in registers
+
+
+def _check_batch_size(batch_size):
+    if not 1 <= int(batch_size) <= MAX_BATCH_SIZE:
+        raise ValueError(f"batch_size={batch_size}: the fused contrastive-loss kernels hold the local batch in registers "
+                         f"and support 1..{MAX_BATCH_SIZE} samples per GPU (the shipped configs use 8 or 32); use more "
+                         "GPUs (data parallel) for a larger global batch")
+
+
 class LayerNorm(nn.Module):
     """gamma is learnable, beta is a constant zero buffer kept in the state_dict (model.py:24-31)."""
 
@@ -202,6 +212,7 @@ class MCA(_FusedModel):
         if dim != D:
             raise AssertionError("encoders hard-wire embedding_dim=512 (encoders.py:79,104,151,178,230): dim must be 512")
         encoder_configs = {k: dict(v) for k, v in dict(encoder_configs).items()}
+        _check_batch_size(batch_size)
         self.batch_size = batch_size
         self.no_fusion = no_fusion
         self.fusion_token, self.global_token = FUSION_TOKEN, GLOBAL_TOKEN
@@ -256,6 +267,7 @@ class EAO(_FusedModel):
         if dim != D:
             raise AssertionError("encoders hard-wire embedding_dim=512 (encoders.py:79,104,151,178,230): dim must be 512")
         encoder_configs = {k: dict(v) for k, v in dict(encoder_configs).items()}
+        _check_batch_size(batch_size)
         self.batch_size = batch_size
         plan = EAOPlan(encoder_configs, list(fusion_combos), fcl, zorro, no_fusion, bimodal_contrastive, non_fusion_fcl)
         self.plan = plan

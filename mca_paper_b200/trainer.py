@@ -40,38 +40,81 @@ class Trainer:
         self._graphs = None
         self._dev_batch: Optional[Dict[str, Dict[str, torch.Tensor]]] = None
         self._pinned: Optional[Dict[str, Dict[str, torch.Tensor]]] = None
+        self._pinned_sets = None
         self.eng.pack_weights()
         self.h2d_bytes = 0
         self.kernel_launches_per_step = None
 
     # ------------------------------------------------------------------------------------------ staging
+    # The host fills a PINNED buffer and enqueues an asynchronous H2D copy from it; the step never synchronises, so the
+    # host can be several steps ahead of the device.  A pinned buffer may therefore only be rewritten once the copy that
+    # reads it has finished: there are two pinned sets, used alternately, each guarded by a CUDA event recorded right
+    # after its H2D copies (the host waits on that event, not on the device as a whole, before refilling the set).
     def _ensure_staging(self, host_batch):
         if self._dev_batch is not None:
             return
         dev = self.eng.device
-        self._dev_batch, self._pinned = {}, {}
+        self._dev_batch, self._pinned_sets = {}, [{}, {}]
         n = 0
         for m, d in host_batch.items():
-            self._dev_batch[m], self._pinned[m] = {}, {}
+            self._dev_batch[m] = {}
+            for ps in self._pinned_sets:
+                ps[m] = {}
             for k, v in d.items():
                 self._dev_batch[m][k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
-                self._pinned[m][k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                for ps in self._pinned_sets:
+                    ps[m][k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
                 n += v.numel() * v.element_size()
+        self._pinned = self._pinned_sets[0]           # the set filled last (h2d() / prefetch() read it)
+        self._pin_free = [None, None]                 # event: the copies out of pinned set i have completed
+        self._pin_next = 0
         self.h2d_bytes = n
 
-    def stage(self, host_batch):
-        """Copy a host batch into the pinned staging area and enqueue its H2D copy on the current stream."""
+    def _fill_pinned(self, host_batch):
+        """Host batch -> the next pinned set (after its previous H2D copies have drained).  Returns the set index."""
         self._ensure_staging(host_batch)
+        i = self._pin_next
+        self._pin_next ^= 1
+        if self._pin_free[i] is not None:
+            self._pin_free[i].synchronize()
         for m, d in host_batch.items():
             for k, v in d.items():
-                self._pinned[m][k].copy_(v)
-                self._dev_batch[m][k].copy_(self._pinned[m][k], non_blocking=True)
+                self._pinned_sets[i][m][k].copy_(v)
+        self._pinned = self._pinned_sets[i]
+        return i
+
+    def _mark_pinned_read(self, i, stream=None):
+        ev = self._pin_free[i]
+        if ev is None:
+            ev = self._pin_free[i] = torch.cuda.Event()
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+
+    def stage(self, host_batch):
+        """Copy a host batch into a pinned staging set and enqueue its H2D copy on the current stream."""
+        i = self._fill_pinned(host_batch)
+        for m, d in self._pinned_sets[i].items():
+            for k, v in d.items():
+                self._dev_batch[m][k].copy_(v, non_blocking=True)
+        self._mark_pinned_read(i)
 
     def h2d(self):
-        """Enqueue only the H2D copies from the (already filled) pinned buffers."""
+        """Enqueue only the H2D copies from the pinned set filled last (the caller keeps it unchanged meanwhile)."""
         for m, d in self._pinned.items():
             for k, v in d.items():
                 self._dev_batch[m][k].copy_(v, non_blocking=True)
+
+    def stage_device(self, dev_batch):
+        """Hand a batch that is already ON THE DEVICE (e.g. the output of collate.DeviceCollator) to the step's input
+        buffers: device-to-device copies on the current stream, no host round trip."""
+        self._ensure_staging(dev_batch)
+        for m, d in dev_batch.items():
+            for k, v in d.items():
+                self._dev_batch[m][k].copy_(v, non_blocking=True)
+
+    def step_device(self, dev_batch):
+        """One optimisation step on a device-resident batch (DeviceCollator output)."""
+        self.stage_device(dev_batch)
+        return self.step_staged()
 
     # ---- pipelined input path: the H2D copy of the next batch runs on a copy stream under the current step
     def _ensure_pipeline(self):
@@ -85,15 +128,22 @@ class Trainer:
         for e in self._consumed:
             e.record()
 
-    def prefetch(self, slot: int):
-        """Start the H2D copy of the pinned batch into staging slot `slot` on the copy stream."""
+    def prefetch(self, slot: int, host_batch=None):
+        """Start the H2D copy of a host batch into device staging slot `slot` on the copy stream.  With `host_batch` the
+        batch is first copied into a free pinned set; without it the pinned set filled last is sent again (the
+        benchmark's fixed synthetic batch)."""
+        if host_batch is not None:
+            i = self._fill_pinned(host_batch)
+        else:
+            i = self._pinned_sets.index(self._pinned)
         self._ensure_pipeline()
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._consumed[slot])
-            for m, d in self._pinned.items():
+            for m, d in self._pinned_sets[i].items():
                 for k, v in d.items():
                     self._slots[slot][m][k].copy_(v, non_blocking=True)
             self._ready[slot].record()
+            self._mark_pinned_read(i, self._copy_stream)
 
     def step_from_slot(self, slot: int):
         """Run one step on the batch prefetched into `slot` (device-to-device hand-over into the graph's inputs)."""
@@ -172,6 +222,7 @@ class Trainer:
                     g.replay()
                 else:
                     g()
+        self.eng.check_p2p()  # host read of a pinned flag: a peer that missed a barrier fails the run, not just the number
         return self.eng.ws["summary"]
 
     def optimizer_state_dict(self):
