@@ -28,20 +28,20 @@ namespace mca {
 constexpr int AT_BM = 128;    // query rows per tile
 constexpr int AT_BN = 128;    // keys per tile
 constexpr int AT_DH = 64;
-constexpr int AT_SOFT_WARPS = 8;                       // 16 query rows per softmax warp (a quad of lanes per row)
+constexpr int AT_SOFT_WARPS = 4;                       // one thread per query row (TMEM lane)
 constexpr int AT_THREADS = (AT_SOFT_WARPS + 2) * 32;   // + TMA warp + MMA warp
 constexpr int AT_TILE_BYTES = AT_BM * AT_DH * 2;       // 16 KB
 constexpr int AT_MAX_KT = 128;                         // key tiles one query tile may visit (the launcher checks)
 constexpr int AT_SCHED_BYTES = AT_MAX_KT * 32;
-constexpr int AT_SMEM = 5 * AT_TILE_BYTES + AT_SCHED_BYTES + 1024;  // Q, 2 x K, 2 x V, schedule (+ alignment slack)
+constexpr int AT_SMEM = 6 * AT_TILE_BYTES + 2 * AT_SCHED_BYTES;  // 2 x Q, 2 x K, 2 x V, 2 schedules
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 #ifdef MCA_TRACE
-// debug-only timeline (-DMCA_TRACE): clock64 stamps of one CTA [role][tile][event] + (start, end, smid) of every CTA
+// debug-only timeline (-DMCA_TRACE): clock64 stamps of one CTA [role][tile][event] + (start, end, smid) of every work item
 __device__ long long g_ftrace[10 * 24 * 8 + 8];
 __device__ long long g_fcta[4096 * 4];
-#define FTR(role, t, e) do { if (blockIdx.x == 5 && blockIdx.y == 3 && (t) < 24) g_ftrace[((role) * 24 + (t)) * 8 + (e)] = clock64(); } while (0)
+#define FTR(role, t, e) do { if (blockIdx.x == 5 && (t) >= 24 && (t) < 48) g_ftrace[((role) * 24 + (t) - 24) * 8 + (e)] = clock64(); } while (0)
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ int smid() { int s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
 #else
@@ -61,10 +61,11 @@ struct AttnFwdArgs {
   __nv_bfloat16* out;        // [B*N, H*64]
   float* lse;                // [B, H, N]
   int N, H, n_kt;
+  int n_items, BH;           // work items = (query tile, sample, head), query tile slow
 };
 
-// One visited key tile of this CTA, staged in shared memory by the prologue so that no role chases global pointers
-// inside the loop (the kt_list -> k_tiles / kt_class / tile_grp / kt_live chain cost ~430 cycles per tile).
+// One visited key tile of a work item, staged in shared memory by the producer warp so that no role chases global
+// pointers inside the loop (the kt_list -> k_tiles / kt_class / tile_grp / kt_live chain cost ~430 cycles per tile).
 struct __align__(16) AtSched {
   int kstart;        // first key position inside the sample
   int klen;          // valid keys of the tile
@@ -72,81 +73,251 @@ struct __align__(16) AtSched {
   int pad;
   uint32_t live[4];  // live-key bits of this (sample, tile)
 };
+struct AtItem { int n_it, b, h, qstart, qlen, item, pad0, pad1; };  // n_it < 0: no more work
 
+// Work queue of the persistent kernel: [0] next item, [1] CTAs that have left.  The last CTA out resets both, so the
+// counters are zero again when the next launch (same stream) starts; the library never allocates device memory.
+__device__ unsigned int g_at_ctr[2];
+
+// The softmax role.  Every shared-memory object it touches is addressed through the static shared window (constant
+// offsets): generic 64-bit pointers for the seven barriers and the schedule cost ~20 registers and, next to the 128
+// registers of the S tile, ~1 KB of spills per thread.
+__device__ __forceinline__ void at_softmax_role(const AttnFwdArgs& a, AtSched* sched_all, const AtItem* s_item, uint64_t* bars,
+                                                uint32_t tmem_base) {
+  uint64_t* item_full = bars + 0;
+  uint64_t* item_empty = bars + 2;
+  uint64_t* s_full = bars + 16;
+  uint64_t* s_empty = bars + 17;
+  uint64_t* p_full = bars + 18;
+  uint64_t* pv_done = bars + 19;
+  uint64_t* o_free = bars + 20;
+  const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    // ===================== softmax / epilogue: thread = query row (TMEM lane) =====================
+    // (Two other layouts were measured at the same 2 CTAs per SM: two threads per row in different warps, 112 us, and a
+    // quad of lanes per row with the 16x256b fragment, 106 us against 111 us for this one; with the work queue added
+    // both no longer fit the 96 registers that 10 warps per CTA leave and spilled: profiles/r2_attn_notes.md.)
+    const int r = warp * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    int g = 0;
+    for (int n = 0;; ++n) {
+      const int slot = n & 1;
+      mbar_wait(&item_full[slot], (n >> 1) & 1);
+      const int n_it = s_item[slot].n_it;
+      if (n_it < 0) break;
+#ifdef MCA_TRACE
+      if (warp == 0 && lane == 0 && s_item[slot].item < 4096) { const int ii = s_item[slot].item; g_fcta[ii * 4] = gtimer(); g_fcta[ii * 4 + 2] = smid(); g_fcta[ii * 4 + 3] = n_it; }
+#endif
+      const AtSched* sched = sched_all + slot * AT_MAX_KT;
+      // allowed key groups of this row (the row may run past the tile's valid rows: it is then never stored)
+      const uint32_t rb = a.rowbits[min(s_item[slot].qstart + r, a.N - 1)];
+      float m2 = -CUDART_INF_F, l_run = 0.f;  // reference maximum (log2 units) and running sum
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const bool masked = sched[it].flags & 1;
+        if (lane == 0) FTR(warp, g, 0);
+        mbar_wait(s_full, g & 1);
+        if (lane == 0) FTR(warp, g, 1);
+        tc_fence_after();
+        uint32_t sv[4][32];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + lane_sel + cc * 32, sv[cc]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite it
+        if (lane == 0) FTR(warp, g, 2);
+        if (masked) {
+          // allowed-key bits: the tile's live-key words, ANDed with the row's visibility of the tile's key group (or of
+          // every key's group for the mixed fusion sub-block tiles)
+          const AtSched e = sched[it];
+          const int grp = (e.flags >> 8) & 255;
+          uint32_t aw[4] = {e.live[0], e.live[1], e.live[2], e.live[3]};
+          if (grp != 255) {
+            if (((rb >> grp) & 1u) == 0) aw[0] = aw[1] = aw[2] = aw[3] = 0;
+          } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              uint32_t bits = 0;
+#pragma unroll 1
+              for (int j = 0; j < 32; ++j) {
+                const int kj = e.kstart + w * 32 + j;
+                if (w * 32 + j < e.klen && ((rb >> a.keygrp[kj]) & 1u)) bits |= 1u << j;
+              }
+              aw[w] &= bits;
+            }
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!((aw[cc] >> i) & 1u)) sv[cc][i] = __float_as_uint(-CUDART_INF_F);
+        }
+        float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[2][i]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[3][i]));
+        }
+        const float t2 = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * LOG2E;
+        const bool grow = t2 > m2 + AT_RESCALE_THRESHOLD;
+        const float m2n = grow ? t2 : m2;
+        const float alpha = grow ? fast_ex2(m2 - m2n) : 1.0f;  // m2 = -inf -> 0
+        if (lane == 0) FTR(warp, g, 3);
+        if (g > 0) {
+          // P of the previous tile has been consumed, O is quiescent (the previous tile may belong to the previous item,
+          // whose epilogue already waited for it: the barrier is then simply found complete)
+          mbar_wait(pv_done, (g - 1) & 1);
+          tc_fence_after();
+          if (it > 0 && __any_sync(0xffffffffu, grow)) {
+#pragma unroll
+            for (int cc = 0; cc < AT_DH / 16; ++cc) {
+              uint32_t ov[16];
+              tmem_ld16(tO + lane_sel + cc * 16, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st16(tO + lane_sel + cc * 16, ov);
+            }
+          }
+        }
+        if (lane == 0) FTR(warp, g, 4);
+        l_run *= alpha;
+        m2 = m2n;
+        const float moff = (m2 == -CUDART_INF_F) ? 0.f : m2;
+        uint64_t sum2 = f2_pack(0.f, 0.f);
+        const uint64_t log2e2 = f2_pack(LOG2E, LOG2E), nmoff2 = f2_pack(-moff, -moff);
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {  // 32 keys -> 16 packed columns
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t0, t1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[hh][2 * j]), __uint_as_float(sv[hh][2 * j + 1])), log2e2, nmoff2), t0, t1);
+            const float p0 = fast_ex2(t0), p1 = fast_ex2(t1);
+            sum2 = f2_add(sum2, f2_pack(p0, p1));
+            pk[j] = pack_bf16x2(p0, p1);
+          }
+          tmem_st16(tP + lane_sel + hh * 16, pk);
+        }
+        {
+          float sum0, sum1;
+          f2_unpack(sum2, sum0, sum1);
+          l_run += sum0 + sum1;
+        }
+        if (lane == 0) FTR(warp, g, 5);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        if (lane == 0) FTR(warp, g, 6);
+      }
+      // ---- item epilogue
+      uint32_t ov[2][32];
+      float lse = CUDART_INF_F;
+      if (n_it > 0) {  // uniform across the CTA
+        mbar_wait(pv_done, (g - 1) & 1);
+        tc_fence_after();
+        tmem_ld32(tO + lane_sel, ov[0]);
+        tmem_ld32(tO + lane_sel + 32, ov[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+      } else {
+        // defined on every path: an undefined accumulator would be live across the whole tile loop above (64 registers
+        // next to the 128 of the S tile = 1 KB of spills per thread)
+#pragma unroll
+        for (int i = 0; i < AT_DH; ++i) ov[i >> 5][i & 31] = 0u;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);  // the next item's first PV may overwrite the accumulator
+      const AtItem I = s_item[slot];
+      const int b = I.b, h = I.h;
+      const long long row0 = static_cast<long long>(b) * a.N;
+      const int qi = I.qstart + r;
+      const bool row_valid = r < I.qlen;
+      if (l_run != 0.f) {
+        const float inv = 1.0f / l_run;
+#pragma unroll
+        for (int i = 0; i < AT_DH; ++i) ov[i >> 5][i & 31] = __float_as_uint(__uint_as_float(ov[i >> 5][i & 31]) * inv);
+        lse = (m2 + log2f(l_run)) * 0.6931471805599453f;
+      } else {  // reference quirk Q4: a row with no live allowed key is uniform over all N keys
+        const float* vm = a.vmean + static_cast<long long>(b) * a.H * AT_DH + h * AT_DH;
+#pragma unroll
+        for (int i = 0; i < AT_DH; ++i) ov[i >> 5][i & 31] = __float_as_uint(vm[i]);
+      }
+      if (row_valid) {
+        __nv_bfloat16* orow = a.out + (row0 + qi) * (a.H * AT_DH) + h * AT_DH;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t* v = &ov[q >> 2][(q & 3) * 8];
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+          w.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+          w.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+          w.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+          reinterpret_cast<uint4*>(orow)[q] = w;
+        }
+        a.lse[(static_cast<long long>(b) * a.H + h) * a.N + qi] = lse;
+      }
+#ifdef MCA_TRACE
+      if (warp == 0 && lane == 0 && I.item < 4096) g_fcta[I.item * 4 + 1] = gtimer();
+#endif
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&item_empty[slot]);
+    }
+    }
+}
+
+// Persistent kernel: 2 CTAs per SM, each pulls (query tile, sample, head) items from the queue, heaviest first.  The
+// pipeline is carried ACROSS items: the producer warp already loads the next item's Q / K / V and stages its schedule
+// while the current item is computed, the MMA warp issues the next item's first QK^T before the current item's last
+// PV, TMEM / barriers / descriptors are set up once per CTA.  (A CTA per item spent ~27 % of its life in launch
+// latency, set-up and the exposed head / tail of its pipeline: profiles/r2_attn_notes.md.)
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = base;
-  uint8_t* sK = base + AT_TILE_BYTES;      // 2 stages
-  uint8_t* sV = base + 3 * AT_TILE_BYTES;  // 2 stages
-  AtSched* sched = reinterpret_cast<AtSched*>(base + 5 * AT_TILE_BYTES);
-  __shared__ uint64_t bars[13];
+  extern __shared__ __align__(1024) uint8_t base[];  // kept in the shared address space: no generic-pointer casts
+  uint8_t* sQ = base;                      // 2 stages (by item parity)
+  uint8_t* sK = base + 2 * AT_TILE_BYTES;  // 2 stages (by tile parity)
+  uint8_t* sV = base + 4 * AT_TILE_BYTES;  // 2 stages
+  AtSched* sched_all = reinterpret_cast<AtSched*>(base + 6 * AT_TILE_BYTES);  // 2 x AT_MAX_KT entries
+  __shared__ uint64_t bars[24];
   __shared__ uint32_t tmem_holder_s;
-  __shared__ int s_nit;
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;   // [2]
-  uint64_t* v_empty = bars + 7;  // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_empty = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* pv_done = bars + 12;
+  __shared__ AtItem s_item[2];
+  uint64_t* item_full = bars + 0;   // [2] schedule + header of the item staged
+  uint64_t* item_empty = bars + 2;  // [2] every consumer is done with the slot
+  uint64_t* q_full = bars + 4;      // [2]
+  uint64_t* q_empty = bars + 6;     // [2]
+  uint64_t* k_full = bars + 8;      // [2]
+  uint64_t* k_empty = bars + 10;    // [2]
+  uint64_t* v_full = bars + 12;     // [2]
+  uint64_t* v_empty = bars + 14;    // [2]
+  uint64_t* s_full = bars + 16;
+  uint64_t* s_empty = bars + 17;
+  uint64_t* p_full = bars + 18;
+  uint64_t* pv_done = bars + 19;
+  uint64_t* o_free = bars + 20;     // the softmax warps have copied the item's O accumulator to registers
   uint32_t* tmem_holder = &tmem_holder_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x % a.H, b = blockIdx.x / a.H;
-#ifdef MCA_TRACE
-  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 0 && cta_lin < 4096) { g_fcta[cta_lin * 4] = gtimer(); g_fcta[cta_lin * 4 + 2] = smid(); g_fcta[cta_lin * 4 + 3] = clock64(); }
-#endif
-  const mca_attn_qtile Q = a.q_tiles[blockIdx.y];
-  const long long row0 = static_cast<long long>(b) * a.N;
 
-  if (warp == AT_SOFT_WARPS) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&k_full[i], 1);
-        mbar_init(&k_empty[i], 1);
-        mbar_init(&v_full[i], 1);
-        mbar_init(&v_empty[i], 1);
-      }
-      mbar_init(s_full, 1);
-      mbar_init(s_empty, AT_SOFT_WARPS * 32);
-      mbar_init(p_full, AT_SOFT_WARPS * 32);
-      mbar_init(pv_done, 1);
-      fence_mbar_init();
-      // the query tile is requested before anything else of the prologue
-      mbar_expect_tx(q_full, AT_TILE_BYTES);
-      tma_load_2d(sQ, &tm_qkv, q_full, h * AT_DH, static_cast<int>(row0 + Q.start));
+  if (warp == AT_SOFT_WARPS && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&item_full[i], 1);
+      mbar_init(&item_empty[i], 1 + AT_SOFT_WARPS);
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
-    __syncwarp();
-    // stage this CTA's schedule: the visited key tiles that hold at least one live key for this sample, in order
-    const uint8_t* cls = a.kt_class + static_cast<long long>(b) * a.n_kt;
-    int n_it = 0;
-    for (int t0 = 0; t0 < Q.kt_cnt; t0 += 32) {
-      const int t = t0 + lane;
-      bool keep = false;
-      AtSched e;
-      if (t < Q.kt_cnt) {
-        const mca_attn_ref ref = a.kt_list[Q.kt_off + t];
-        const int c = cls[ref.tile];
-        keep = c != 2;
-        const mca_attn_tile K = a.k_tiles[ref.tile];
-        const int grp = a.tile_grp[ref.tile];
-        const bool masked = (ref.flags & 1) || c == 1 || K.len < AT_BN || grp == 255;
-        const uint4 lw = *reinterpret_cast<const uint4*>(a.kt_live + (static_cast<long long>(b) * a.n_kt + ref.tile) * 4);
-        e.kstart = K.start, e.klen = K.len, e.flags = (masked ? 1 : 0) | (grp << 8), e.pad = 0;
-        e.live[0] = lw.x, e.live[1] = lw.y, e.live[2] = lw.z, e.live[3] = lw.w;
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, keep);
-      if (keep) sched[n_it + __popc(m & ((1u << lane) - 1u))] = e;
-      n_it += __popc(m);
-    }
-    if (lane == 0) s_nit = n_it;
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, AT_SOFT_WARPS * 32);
+    mbar_init(p_full, AT_SOFT_WARPS * 32);
+    mbar_init(pv_done, 1);
+    mbar_init(o_free, AT_SOFT_WARPS);
+    fence_mbar_init();
   }
   if (warp == AT_SOFT_WARPS + 1) tmem_alloc(tmem_holder, 256);
   tc_fence_before();
@@ -154,264 +325,182 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
-  const int n_it = s_nit;
 
   if (warp == AT_SOFT_WARPS) {
-    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
-    for (int it = 0; it < n_it; ++it) {
-      const int krow = static_cast<int>(row0 + sched[it].kstart);
-      const int st = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      if (lane == 0) FTR(9, it, 0);
-      mbar_wait(&k_empty[st], ph ^ 1);
-      if (lane == 0) FTR(9, it, 1);
+    // ===================== producer: work queue, schedule staging, TMA loads (whole warp loops) =====================
+    int g = 0;  // running tile counter of this CTA (K / V ring position)
+    for (int n = 0;; ++n) {
+      const int slot = n & 1;
+      const uint32_t iph = (n >> 1) & 1;
+      mbar_wait(&item_empty[slot], iph ^ 1);
+      unsigned int item = 0;
+      if (lane == 0) item = atomicAdd(&g_at_ctr[0], 1u);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= static_cast<unsigned int>(a.n_items)) {
+        if (lane == 0) {
+          s_item[slot].n_it = -1;
+          mbar_arrive(&item_full[slot]);
+        }
+        break;
+      }
+      const int y = static_cast<int>(item) / a.BH, bh = static_cast<int>(item) % a.BH;
+      const int b = bh / a.H, h = bh % a.H;
+      const mca_attn_qtile Q = a.q_tiles[y];
+      const long long row0 = static_cast<long long>(b) * a.N;
+      // the query tile is requested before the schedule is staged
+      mbar_wait(&q_empty[slot], iph ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&k_full[st], AT_TILE_BYTES);
-        tma_load_2d(sK + st * AT_TILE_BYTES, &tm_qkv, &k_full[st], a.H * AT_DH + h * AT_DH, krow);
+        mbar_expect_tx(&q_full[slot], AT_TILE_BYTES);
+        tma_load_2d(sQ + slot * AT_TILE_BYTES, &tm_qkv, &q_full[slot], h * AT_DH, static_cast<int>(row0 + Q.start));
       }
       __syncwarp();
-      mbar_wait(&v_empty[st], ph ^ 1);
-      if (lane == 0) FTR(9, it, 2);
-      if (elect_one()) {
-        mbar_expect_tx(&v_full[st], AT_TILE_BYTES);
-        tma_load_2d(sV + st * AT_TILE_BYTES, &tm_qkv, &v_full[st], 2 * a.H * AT_DH + h * AT_DH, krow);
+      // stage the item's schedule: the visited key tiles that hold at least one live key for this sample, in order
+      AtSched* sched = sched_all + slot * AT_MAX_KT;
+      const uint8_t* cls = a.kt_class + static_cast<long long>(b) * a.n_kt;
+      int n_it = 0;
+      for (int t0 = 0; t0 < Q.kt_cnt; t0 += 32) {
+        const int t = t0 + lane;
+        bool keep = false;
+        AtSched e;
+        if (t < Q.kt_cnt) {
+          const mca_attn_ref ref = a.kt_list[Q.kt_off + t];
+          const int c = cls[ref.tile];
+          keep = c != 2;
+          const mca_attn_tile K = a.k_tiles[ref.tile];
+          const int grp = a.tile_grp[ref.tile];
+          const bool masked = (ref.flags & 1) || c == 1 || K.len < AT_BN || grp == 255;
+          const uint4 lw = *reinterpret_cast<const uint4*>(a.kt_live + (static_cast<long long>(b) * a.n_kt + ref.tile) * 4);
+          e.kstart = K.start, e.klen = K.len, e.flags = (masked ? 1 : 0) | (grp << 8), e.pad = 0;
+          e.live[0] = lw.x, e.live[1] = lw.y, e.live[2] = lw.z, e.live[3] = lw.w;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) sched[n_it + __popc(m & ((1u << lane) - 1u))] = e;
+        n_it += __popc(m);
       }
       __syncwarp();
+      if (lane == 0) {
+        s_item[slot] = AtItem{n_it, b, h, Q.start, Q.len, static_cast<int>(item), 0, 0};
+        mbar_arrive(&item_full[slot]);
+      }
+      __syncwarp();
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const int krow = static_cast<int>(row0 + sched[it].kstart);
+        const int st = g & 1;
+        const uint32_t ph = (g >> 1) & 1;
+        if (lane == 0) FTR(9, g, 0);
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (lane == 0) FTR(9, g, 1);
+        if (elect_one()) {
+          mbar_expect_tx(&k_full[st], AT_TILE_BYTES);
+          tma_load_2d(sK + st * AT_TILE_BYTES, &tm_qkv, &k_full[st], a.H * AT_DH + h * AT_DH, krow);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (lane == 0) FTR(9, g, 2);
+        if (elect_one()) {
+          mbar_expect_tx(&v_full[st], AT_TILE_BYTES);
+          tma_load_2d(sV + st * AT_TILE_BYTES, &tm_qkv, &v_full[st], 2 * a.H * AT_DH + h * AT_DH, krow);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp == AT_SOFT_WARPS + 1) {
     // ===================== MMA issuer =====================
     // The whole warp runs the loop and the waits (convergent code keeps the descriptors in uniform registers, so a
-    // tcgen05.mma costs one uniform add); one elected lane issues the MMAs and commits.
+    // tcgen05.mma costs one uniform add); one elected lane issues the MMAs and commits.  The loop is flat over the tiles
+    // of successive items: QK^T of tile g is issued before PV of tile g - 1, also across an item boundary.
     constexpr uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, false, false);
     constexpr uint32_t idesc_o = make_idesc_bf16(AT_BM, AT_DH, false, true);
     const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
     const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
     const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
-    auto issue_pv = [&](int j) {
-      const int st = j & 1;
+    int pend_g = -1, pend_n = 0;   // tile whose PV is still to be issued, and its item
+    bool pend_first = false;
+    auto issue_pv = [&]() {
+      const int j = pend_g, st = j & 1;
       mbar_wait(&v_full[st], (j >> 1) & 1);
       if (lane == 0) FTR(8, j, 4);
       mbar_wait(p_full, j & 1);
       if (lane == 0) FTR(8, j, 5);
+      // the first PV of an item overwrites the accumulator: the previous item's O must have been read out
+      if (pend_first && pend_n > 0) mbar_wait(o_free, (pend_n - 1) & 1);
       tc_fence_after();
       const uint64_t dv = dv0 + static_cast<uint64_t>((st * AT_TILE_BYTES) >> 4);
+      const uint32_t acc0 = pend_first ? 0u : 1u;
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k)
-          umma_bf16_ts(tO, tP + k * 8, dv + k * (2048 >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < AT_BN / 16; ++k) umma_bf16_ts(tO, tP + k * 8, dv + k * (2048 >> 4), idesc_o, k > 0 ? 1u : acc0);
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
       }
       __syncwarp();
       if (lane == 0) FTR(8, j, 6);
     };
-    mbar_wait(q_full, 0);
-    for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
-      if (lane == 0) FTR(8, it, 0);
-      mbar_wait(&k_full[st], (it >> 1) & 1);
-      if (lane == 0) FTR(8, it, 1);
-      mbar_wait(s_empty, (it & 1) ^ 1);
-      if (lane == 0) FTR(8, it, 2);
-      tc_fence_after();
-      const uint64_t dk = dk0 + static_cast<uint64_t>((st * AT_TILE_BYTES) >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < AT_DH / 16; ++k) umma_bf16(tS, dq0 + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&k_empty[st]);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-      if (lane == 0) FTR(8, it, 3);
-      if (it > 0) issue_pv(it - 1);
-    }
-    if (n_it > 0) issue_pv(n_it - 1);
-  } else {
-    // ===================== softmax / epilogue: warp = 16 query rows, a quad of lanes per row ======================
-    // Fragment of tcgen05.ld.16x256b (the m16n8 accumulator layout): lane i holds rows i/4 and i/4 + 8 of the warp's
-    // 16 TMEM lanes and columns 8j + 2(i%4) + {0,1}: row maxima / sums are two quad shuffles, no shared memory and no
-    // barrier between warps.  Eight softmax warps per CTA (two CTAs per SM): four independent softmax warps per
-    // scheduler; one warp per scheduler reaches ~8 of the SM's 16 exp2 per clock, four reach ~14 (ubench/mufu_rate.cu).
-    const int wq = warp & 3;                 // TMEM lane quarter this warp may access
-    const int lbase = wq * 32 + (warp >> 2) * 16;  // first of the warp's 16 lanes (= query rows of the tile)
-    const int qd = lane & 3;                 // position inside the quad
-    const int rA = lbase + (lane >> 2), rB = rA + 8;
-    const int qiA = Q.start + rA, qiB = Q.start + rB;  // rows inside the sample (may run past the tile: never stored)
-    const uint32_t rbA = a.rowbits[min(qiA, a.N - 1)], rbB = a.rowbits[min(qiB, a.N - 1)];
-    const uint32_t lsel = static_cast<uint32_t>(lbase) << 16;
-    float m2A = -CUDART_INF_F, m2B = -CUDART_INF_F;  // reference maxima (log2 units)
-    float lA = 0.f, lB = 0.f;                        // partial row sums of this lane's columns
-    for (int it = 0; it < n_it; ++it) {
-      const AtSched e = sched[it];
-      const bool masked = e.flags & 1;
-      uint32_t awA[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-      uint32_t awB[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-      if (masked) {
-        const int grp = (e.flags >> 8) & 255;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) awA[w] = awB[w] = e.live[w];
-        if (grp != 255) {
-          if (((rbA >> grp) & 1u) == 0) awA[0] = awA[1] = awA[2] = awA[3] = 0;
-          if (((rbB >> grp) & 1u) == 0) awB[0] = awB[1] = awB[2] = awB[3] = 0;
-        } else {
-          // mixed key groups (the fusion sub-blocks): per-key visibility; only this lane's columns are needed
-#pragma unroll 1
-          for (int j = 0; j < 16; ++j) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int kk = 8 * j + 2 * qd + c;
-              const uint32_t g = kk < e.klen ? a.keygrp[e.kstart + kk] : 31u;
-              const uint32_t bit = 1u << (kk & 31);
-              if (kk >= e.klen || !((rbA >> g) & 1u)) awA[kk >> 5] &= ~bit;
-              if (kk >= e.klen || !((rbB >> g) & 1u)) awB[kk >> 5] &= ~bit;
-            }
-          }
-        }
-#pragma unroll
-        for (int w = 0; w < 4; ++w) awA[w] >>= 2 * qd, awB[w] >>= 2 * qd;  // bit 8(j&3) + c = column 8j + 2 qd + c
-      }
-      if (lane == 0) FTR(warp, it, 0);
-      mbar_wait(s_full, it & 1);
-      if (lane == 0) FTR(warp, it, 1);
-      tc_fence_after();
-      uint32_t sv[2][32];  // sv[hh][4 jj + {0,1}] = row A, [4 jj + {2,3}] = row B, columns 64 hh + 8 jj + 2 qd + {0,1}
-      tmem_ld16x256b_x8(tS + lsel, sv[0]);
-      tmem_ld16x256b_x8(tS + lsel + 64, sv[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite it
-      if (lane == 0) FTR(warp, it, 2);
-      if (masked) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int w = hh * 2 + (jj >> 2), sh = 8 * (jj & 3);
-            if (!((awA[w] >> sh) & 1u)) sv[hh][4 * jj + 0] = __float_as_uint(-CUDART_INF_F);
-            if (!((awA[w] >> (sh + 1)) & 1u)) sv[hh][4 * jj + 1] = __float_as_uint(-CUDART_INF_F);
-            if (!((awB[w] >> sh) & 1u)) sv[hh][4 * jj + 2] = __float_as_uint(-CUDART_INF_F);
-            if (!((awB[w] >> (sh + 1)) & 1u)) sv[hh][4 * jj + 3] = __float_as_uint(-CUDART_INF_F);
-          }
-      }
-      float mxA = -CUDART_INF_F, mxB = -CUDART_INF_F;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          mxA = fmaxf(mxA, fmaxf(__uint_as_float(sv[hh][4 * jj]), __uint_as_float(sv[hh][4 * jj + 1])));
-          mxB = fmaxf(mxB, fmaxf(__uint_as_float(sv[hh][4 * jj + 2]), __uint_as_float(sv[hh][4 * jj + 3])));
-        }
-      mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 1));
-      mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 1));
-      mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 2));
-      mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
-      const float tA = mxA * LOG2E, tB = mxB * LOG2E;
-      const bool growA = tA > m2A + AT_RESCALE_THRESHOLD, growB = tB > m2B + AT_RESCALE_THRESHOLD;
-      const float nA = growA ? tA : m2A, nB = growB ? tB : m2B;
-      const float alphaA = growA ? fast_ex2(m2A - nA) : 1.0f;  // m2 = -inf -> 0
-      const float alphaB = growB ? fast_ex2(m2B - nB) : 1.0f;
-      if (lane == 0) FTR(warp, it, 3);
-      lA *= alphaA, lB *= alphaB;
-      m2A = nA, m2B = nB;
-      const float offA = (m2A == -CUDART_INF_F) ? 0.f : m2A, offB = (m2B == -CUDART_INF_F) ? 0.f : m2B;
-      const uint64_t log2e2 = f2_pack(LOG2E, LOG2E), noffA = f2_pack(-offA, -offA), noffB = f2_pack(-offB, -offB);
-      uint64_t sumA = f2_pack(0.f, 0.f), sumB = f2_pack(0.f, 0.f);
-      uint32_t pk[32];  // 16x128b fragment of the bf16-packed P tile: pk[2 j] = row A, pk[2 j + 1] = row B, column 4 j + qd
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          float a0, a1, b0, b1;
-          f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[hh][4 * jj]), __uint_as_float(sv[hh][4 * jj + 1])), log2e2, noffA), a0, a1);
-          f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[hh][4 * jj + 2]), __uint_as_float(sv[hh][4 * jj + 3])), log2e2, noffB), b0, b1);
-          const float pa0 = fast_ex2(a0), pa1 = fast_ex2(a1), pb0 = fast_ex2(b0), pb1 = fast_ex2(b1);
-          sumA = f2_add(sumA, f2_pack(pa0, pa1));
-          sumB = f2_add(sumB, f2_pack(pb0, pb1));
-          pk[2 * (hh * 8 + jj)] = pack_bf16x2(pa0, pa1);
-          pk[2 * (hh * 8 + jj) + 1] = pack_bf16x2(pb0, pb1);
-        }
-      {
-        float s0, s1;
-        f2_unpack(sumA, s0, s1);
-        lA += s0 + s1;
-        f2_unpack(sumB, s0, s1);
-        lB += s0 + s1;
-      }
-      if (lane == 0) FTR(warp, it, 4);
-      if (it > 0) {
-        mbar_wait(pv_done, (it - 1) & 1);  // P of the previous tile has been consumed, O is quiescent
+    int g = 0;
+    for (int n = 0;; ++n) {
+      const int slot = n & 1;
+      const uint32_t iph = (n >> 1) & 1;
+      mbar_wait(&item_full[slot], iph);
+      const int n_it = s_item[slot].n_it;
+      if (n_it < 0) break;
+      if (n_it > 0) mbar_wait(&q_full[slot], iph);
+      const uint64_t dq = dq0 + static_cast<uint64_t>((slot * AT_TILE_BYTES) >> 4);
+      for (int it = 0; it < n_it; ++it, ++g) {
+        const int st = g & 1;
+        if (lane == 0) FTR(8, g, 0);
+        mbar_wait(&k_full[st], (g >> 1) & 1);
+        if (lane == 0) FTR(8, g, 1);
+        mbar_wait(s_empty, (g & 1) ^ 1);
+        if (lane == 0) FTR(8, g, 2);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, growA || growB)) {
-          uint32_t ov[32];
-          tmem_ld16x256b_x8(tO + lsel, ov);
-          tmem_ld_wait();
+        const uint64_t dk = dk0 + static_cast<uint64_t>((st * AT_TILE_BYTES) >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            ov[4 * jj] = __float_as_uint(__uint_as_float(ov[4 * jj]) * alphaA);
-            ov[4 * jj + 1] = __float_as_uint(__uint_as_float(ov[4 * jj + 1]) * alphaA);
-            ov[4 * jj + 2] = __float_as_uint(__uint_as_float(ov[4 * jj + 2]) * alphaB);
-            ov[4 * jj + 3] = __float_as_uint(__uint_as_float(ov[4 * jj + 3]) * alphaB);
-          }
-          tmem_st16x256b_x8(tO + lsel, ov);
+          for (int k = 0; k < AT_DH / 16; ++k) umma_bf16(tS, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&k_empty[st]);
+          if (it == n_it - 1) umma_commit(&q_empty[slot]);  // the item's last read of its Q tile
+          umma_commit(s_full);
+        }
+        __syncwarp();
+        if (lane == 0) FTR(8, g, 3);
+        if (pend_g >= 0) issue_pv();
+        pend_g = g, pend_n = n, pend_first = it == 0;
+      }
+      if (n_it == 0 && elect_one()) mbar_arrive(&q_empty[slot]);  // nothing read the (loaded) Q tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&item_empty[slot]);
+      // The last PV of the item is normally issued behind the next item's first QK^T.  It may only be deferred when
+      // that item is already staged and has tiles: the softmax warps wait for this PV before they release the item
+      // slot, and the producer needs a free slot to stage anything further (a run of empty items would deadlock).
+      if (pend_g >= 0) {
+        const int ns = (n + 1) & 1;
+        bool defer = mbar_try_wait(&item_full[ns], ((n + 1) >> 1) & 1);
+        defer = __shfl_sync(0xffffffffu, defer ? 1 : 0, 0) != 0;
+        if (defer) defer = s_item[ns].n_it > 0;
+        if (!defer) {
+          issue_pv();
+          pend_g = -1;
         }
       }
-      if (lane == 0) FTR(warp, it, 5);
-      tmem_st16x128b_x16(tP + lsel, pk);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_full);
-      if (lane == 0) FTR(warp, it, 6);
     }
-    // ---- epilogue: normalise and store the warp's 16 rows (each lane: 2 rows x 16 columns)
-    uint32_t ov[32];
-    if (n_it > 0) {  // uniform across the CTA
-      mbar_wait(pv_done, (n_it - 1) & 1);
-      tc_fence_after();
-      tmem_ld16x256b_x8(tO + lsel, ov);
-      tmem_ld_wait();
-    }
-    lA += __shfl_xor_sync(0xffffffffu, lA, 1);
-    lB += __shfl_xor_sync(0xffffffffu, lB, 1);
-    lA += __shfl_xor_sync(0xffffffffu, lA, 2);
-    lB += __shfl_xor_sync(0xffffffffu, lB, 2);
-    const float* vm = a.vmean + static_cast<long long>(b) * a.H * AT_DH + h * AT_DH;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const float l_tot = rr ? lB : lA;
-      const float m2 = rr ? m2B : m2A;
-      const int r = rr ? rB : rA, qi = rr ? qiB : qiA;
-      float lse = CUDART_INF_F;
-      float inv = 0.f;
-      if (l_tot != 0.f) {
-        inv = 1.0f / l_tot;
-        lse = (m2 + log2f(l_tot)) * 0.6931471805599453f;
-      }
-      if (r < Q.len) {
-        __nv_bfloat16* orow = a.out + (row0 + qi) * (a.H * AT_DH) + h * AT_DH;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int c = 8 * jj + 2 * qd;
-          float o0, o1;
-          if (l_tot != 0.f) {
-            o0 = __uint_as_float(ov[4 * jj + 2 * rr]) * inv, o1 = __uint_as_float(ov[4 * jj + 2 * rr + 1]) * inv;
-          } else {  // reference quirk Q4: a row with no live allowed key is uniform over all N keys
-            o0 = vm[c], o1 = vm[c + 1];
-          }
-          *reinterpret_cast<uint32_t*>(orow + c) = pack_bf16x2(o0, o1);
-        }
-        if (qd == 0) a.lse[(static_cast<long long>(b) * a.H + h) * a.N + qi] = lse;
-      }
-    }
+    if (pend_g >= 0) issue_pv();
+  } else {
+    at_softmax_role(a, sched_all, s_item, bars, tmem_base);
   }
   tc_fence_before();
   __syncthreads();
-#ifdef MCA_TRACE
-  if (threadIdx.x == 0 && cta_lin < 4096) g_fcta[cta_lin * 4 + 1] = gtimer();
-  if (threadIdx.x == 0 && blockIdx.x == 5 && blockIdx.y == 3) { g_ftrace[10 * 24 * 8] = g_fcta[cta_lin * 4 + 3]; g_ftrace[10 * 24 * 8 + 1] = clock64(); }
-#endif
   if (warp == AT_SOFT_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
+  }
+  // last CTA out resets the work queue for the next launch
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&g_at_ctr[1], 1u) == gridDim.x - 1) {
+      g_at_ctr[0] = 0u;
+      g_at_ctr[1] = 0u;
+      __threadfence();
+    }
   }
 }
 
@@ -465,9 +554,10 @@ extern "C" int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int 
   dim3 gv((N + VM_ROWS - 1) / VM_ROWS, B);
   vmean_kernel<<<gv, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ld, 2 * H * AT_DH, H * AT_DH, N,
                                        any_absent, vmean);
+  const int n_items = B * H * n_qt;  // item index = query tile (slow, heaviest first) x (sample, head)
   AttnFwdArgs a{q_tiles, kt_list, k_tiles, rowbits, keygrp, tile_grp, kt_class, kt_live, vmean,
-                reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, n_kt};
-  dim3 grid(B * H, n_qt);  // x fastest: every (sample, head) of the heaviest query tile is dispatched first
+                reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, n_kt, n_items, B * H};
+  const int grid = n_items < 2 * num_sms() ? n_items : 2 * num_sms();  // persistent: two CTAs per SM pull from the queue
   attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, a);
   return check_launch();
 }

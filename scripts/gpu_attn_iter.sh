@@ -10,5 +10,5 @@ tail -4 $OUT/r2_t_$TAG.log
 timeout 200 python scripts/gpu_attn_time.py > $OUT/r2_time_$TAG.log 2>&1; cat $OUT/r2_time_$TAG.log
 if [ "$2" = "trace" ]; then
   MCA_LIB=$PWD/mca_paper_b200/csrc/libmca_b200_trace.so timeout 300 python scripts/gpu_attn_trace.py > $OUT/r2_trace_$TAG.log 2>&1
-  echo "trace rc=$?"; grep -E "^t= (5|6) |fwd\]|bwd\]" $OUT/r2_trace_$TAG.log | head -60
+  echo "trace rc=$?"; grep -E "^t= ?(5|6|11|12|13) |fwd\]|bwd\]" $OUT/r2_trace_$TAG.log | head -60
 fi

@@ -62,16 +62,11 @@ ev = a[:NR * 24 * 8].reshape(NR, 24, 8)
 names = {i: f"SW{i} " for i in range(8)}
 names.update({8: "MMA ", 9: "TMA "})
 print("SWn: top s_full ld_done max_done exp_done pv_done/rescale p_full | MMA: top k_full s_empty S_issued v_full p_full PV_issued | TMA: top k_empty v_empty")
-for t in range(13):
+for t in range(24):
     for role in (8, 0, 1, 2, 3, 4, 5, 6, 7, 9):
         row = ev[role, t]
         print(f"t={t:2d} {names[role]}: " + " ".join(f"{int(x - t0):7d}" if x else "      -" for x in row))
-c = np.array(ct[:], dtype=np.int64).reshape(4096, 4)
-c[:, 3] = 0
-nq = int(eng.q_tiles.shape[0])
-qt = eng.q_tiles.cpu().numpy()
-for y in range(nq):
-    c[y * eng.B * eng.H:(y + 1) * eng.B * eng.H, 3] = int(qt[y][3])
+c = np.array(ct[:], dtype=np.int64).reshape(4096, 4)   # per work item: (start, end, smid, n_it)
 cta_summary("fwd", c)
 
 # ------------------------------------------------------------------ backward
