@@ -81,9 +81,9 @@ g = a[4 * 16 * 16:]
 t0 = g[0]
 print("BWD global: setup_done=0 kv_full=%d q0_full=%d epi_wg0=%d epi_wg1=%d end_wg0=%d end_wg1=%d cta_end=%d" % tuple(int(x - t0) for x in g[1:8]))
 ev = a[:4 * 16 * 16].reshape(4, 16, 16)[:, :, :16]
-names = {0: "WG0", 1: "WG1", 2: "MMA"}
+names = {0: "WG0", 1: "WG1", 2: "MMA", 3: "MMB"}
 for t in range(13):
-    for role in (2, 0, 1):
+    for role in (2, 3, 0, 1):
         row = ev[role, t]
         print(f"t={t:2d} {names[role]}: " + " ".join(f"{int(x - t0):7d}" if x else "      -" for x in row))
 cb = (ctypes.c_longlong * n_cta)()

@@ -78,14 +78,19 @@ int main() {
       for (int b_mn : {0, 1})
         for (int n : {64, 128, 256}) {
           if (n_acc * n > 448) continue;
-          const int grid = 148, lds = 0;
-          mma_rate_kernel<<<grid, 160, 96 * 1024>>>(n, a_mode, b_mn, 64, 0, d, n_acc);  // warm
-          mma_rate_kernel<<<grid, 160, 96 * 1024>>>(n, a_mode, b_mn, iters, lds, d, n_acc);
-          long long c = 0;
-          cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
-          if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
-          printf("accumulators %d  M=128 N=%3d K=16  %-16s B %-8s : %7.1f cycles/MMA  (ideal %d)\n", n_acc, n, am[a_mode],
-                 b_mn ? "MN-major" : "K-major", double(c) / iters, 128 * n / 256);
+          const int grid = 148;
+          double res[3];
+          int li = 0;
+          for (int lds : {0, 3000, 6001}) {  // 0: none; even: 128-bit loads only; odd: loads + stores (4 warps)
+            mma_rate_kernel<<<grid, 160, 96 * 1024>>>(n, a_mode, b_mn, 64, 0, d, n_acc);  // warm
+            mma_rate_kernel<<<grid, 160, 96 * 1024>>>(n, a_mode, b_mn, iters, lds, d, n_acc);
+            long long c = 0;
+            cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+            res[li++] = double(c) / iters;
+          }
+          printf("accumulators %d  M=128 N=%3d K=16  %-16s B %-8s : %7.1f cycles/MMA  (ideal %d)   with LDS traffic %7.1f   with LDS+STS traffic %7.1f\n",
+                 n_acc, n, am[a_mode], b_mn ? "MN-major" : "K-major", res[0], 128 * n / 256, res[1], res[2]);
         }
   return 0;
 }
