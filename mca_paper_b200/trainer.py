@@ -66,6 +66,7 @@ class Trainer:
                     ps[m][k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
                 n += v.numel() * v.element_size()
         self._pinned = self._pinned_sets[0]           # the set filled last (h2d() / prefetch() read it)
+        self._pin_last = 0
         self._pin_free = [None, None]                 # event: the copies out of pinned set i have completed
         self._pin_next = 0
         self.h2d_bytes = n
@@ -81,6 +82,7 @@ class Trainer:
             for k, v in d.items():
                 self._pinned_sets[i][m][k].copy_(v)
         self._pinned = self._pinned_sets[i]
+        self._pin_last = i
         return i
 
     def _mark_pinned_read(self, i, stream=None):
@@ -135,7 +137,7 @@ class Trainer:
         if host_batch is not None:
             i = self._fill_pinned(host_batch)
         else:
-            i = self._pinned_sets.index(self._pinned)
+            i = self._pin_last
         self._ensure_pipeline()
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._consumed[slot])

@@ -123,7 +123,8 @@ def test_save_state_load_state_resumes_identically(tmp_path):
     for _ in range(3):
         tr.step(batch)
     out = K.save_state(tr, str(tmp_path / "ckpt"))
-    assert sorted(os.listdir(out)) == ["model.safetensors", "optimizer.bin", "random_states_0.pkl", "scheduler.bin"]
+    assert sorted(os.listdir(out)) == ["mca_b200_state_0.json", "model.safetensors", "optimizer.bin",
+                                       "random_states_0.pkl", "scheduler.bin"]
     s4 = tr.step(batch).clone()
     after = {k: v.detach().clone() for k, v in model.state_dict().items()}
 
