@@ -92,8 +92,18 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def cpu_training_step_fn(cfg_name: str, batch_size: int):
-    """The reference algorithm (oracle port, oracle/mca_oracle.py) as a CPU training step closure."""
+def _to_dev(obj, dev):
+    if isinstance(obj, torch.Tensor):
+        return obj.to(dev)
+    if isinstance(obj, dict):
+        return {k: _to_dev(v, dev) for k, v in obj.items()}
+    return obj
+
+
+def cpu_training_step_fn(cfg_name: str, batch_size: int, device: str = "cpu", variant: str = "full", seed: int = 1):
+    """The reference algorithm (oracle port, oracle/mca_oracle.py: plain torch fp32 ops + autograd) as a training step
+    closure.  device="cpu": the reference's CPU path (cpu_baseline / --impl reference); device="cuda": the same eager
+    fp32 program on the B200 (eager_gpu_baseline, the bar SURVEY.md §6 names)."""
     from mca_paper_b200 import config as C, synthetic as S
     from oracle import mca_oracle as O
 
@@ -105,13 +115,13 @@ def cpu_training_step_fn(cfg_name: str, batch_size: int):
     torch.manual_seed(43)
     model = (EAO if kw.get("eao") else MCA)(**kw)  # parameter container only (CPU); arithmetic below is the oracle's
     oracle_forward = O.eao_forward if kw.get("eao") else O.mca_forward
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sd = {k: v.detach().clone().to(device) for k, v in model.state_dict().items()}
     names = [k for k, _ in model.named_parameters()]
     params = [sd[k].requires_grad_(True) for k in names]
     m = [torch.zeros_like(p) for p in params]
     v = [torch.zeros_like(p) for p in params]
-    tables = O.static_tables(kw)
-    batch = S.make_batch(cfg, seed=1, variant="full", batch_size=batch_size)
+    tables = _to_dev(O.static_tables(kw), device)
+    batch = _to_dev(S.make_batch(cfg, seed=seed, variant=variant, batch_size=batch_size), device)
     state = {"step": 0}
 
     def step():
@@ -134,8 +144,8 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    bs = 2
-    step = cpu_training_step_fn("CMU_config1", bs)
+    bs = 8  # the configured batch (configs/CMU_config1.yaml:14): the same step the B200 arm times
+    step = cpu_training_step_fn(args.config, bs, variant=args.variant)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -143,19 +153,62 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     val = args.steps * bs / dt
-    sample = f"{bs} samples per step (fwd+bwd+clip+AdamW, fp32, torch CPU ops) of CMU_config1 shape; batch_size=8 does not fit the time bound"
+    sample = (f"every step = one full training step (fwd+bwd+clip+AdamW, fp32, torch CPU ops on {cores} threads) on the same "
+              f"{bs}-sample {args.config} batch the B200 arm uses")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CMU_config1 MCA training step (COVAREP 1500x74, FACET 450x35, OpenFace 450x713, GloVe 50x300, "
-                               "88 fusion tokens, 5 layers, 14 InfoNCE pairs)", "batch_per_step": bs},
+        "config": {"workload": workload_string(args.config, args.variant), "global_batch": bs, "batch_per_step": bs},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference cannot be installed (torchmultimodal/yacs/accelerate absent, no network); this arm times "
                 "oracle/mca_oracle.py, the CPU restatement pinned against the live reference (tests/golden)",
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_string(cfg_name: str, variant: str) -> str:
+    """Workload description from the config itself (modalities, shapes, losses), identical for both arms."""
+    from mca_paper_b200 import config as C
+    from mca_paper_b200.plan import EAOPlan, StaticPlan
+
+    cfg = C.named_config(cfg_name)
+    kw = C.get_model_config(cfg)
+    enc = kw["encoder_configs"]
+    mods = ", ".join(f"{n} {e['max_tokens']}x{e.get('input_size', 1)}" for n, e in enc.items())
+    if kw.get("eao"):
+        pl = EAOPlan(enc, list(kw.get("fusion_combos", (4, 5))), kw.get("fcl", False), kw.get("zorro", False),
+                     kw.get("no_fusion", True), kw.get("bimodal_contrastive", False), kw.get("non_fusion_fcl", False))
+        return (f"{cfg_name} EAO training step, B={cfg['batch_size']} per GPU ({mods}; {pl.R} passes stacked "
+                f"block-diagonally -> N={pl.N} tokens per sample, d=512, {kw['depth']} layers, mean pooling, {pl.n_pairs} InfoNCE "
+                f"pairs), variant={variant}")
+    pl = StaticPlan(enc, kw.get("num_fusion_tokens", 16), list(kw.get("fusion_combos", (4, 5))), kw.get("fcl", False),
+                    kw.get("zorro", False), kw.get("no_fusion", False), kw.get("bimodal_contrastive", False),
+                    kw.get("non_fusion_fcl", False))
+    kind = "MMA" if kw.get("zorro") else "MCA"
+    return (f"{cfg_name} {kind} training step, B={cfg['batch_size']} per GPU ({mods}; {pl.F} fusion tokens -> N={pl.N}, d=512, "
+            f"{kw['depth']} layers, {pl.n_pairs} InfoNCE pairs), variant={variant}")
+
+
+def live_allowed_pairs(plan, host_batch) -> float:
+    """Mean over the batch of the (query, key) pairs parity needs: statically allowed AND key not padded (every query row
+    is computed, padded ones included: SURVEY.md H1).  Equals plan.allowed_pairs for an unpadded batch."""
+    import numpy as np
+
+    pads = []
+    for name in plan.names:
+        d = host_batch[name]
+        if "attention_mask" in d:
+            pads.append(d["attention_mask"].to(torch.bool).numpy())
+        else:  # PatchEncoder derives its own mask: treat as live
+            pads.append(np.zeros((next(iter(d.values())).shape[0], plan.lengths[plan.names.index(name)]), dtype=bool))
+    B = pads[0].shape[0]
+    if getattr(plan, "eao", False):
+        return float(plan.allowed_pairs)
+    pad = np.concatenate(pads + [np.zeros((B, plan.F), dtype=bool)], axis=1)       # [B, N]
+    allowed_per_key = (~plan.attn_mask).sum(axis=0).astype(np.float64)              # queries that may see key k
+    return float(((~pad) * allowed_per_key[None, :]).sum() / B)
 
 
 def ncu_traffic(entry_point: str):
@@ -349,6 +402,7 @@ def main():
     loss_pinned = loss_pin2[(args.steps - 1) & 1]
     clocks = sampler.stop() if sampler is not None else None
     final_loss = float(loss_pinned[0])
+    h2d_bytes = trainer.h2d_bytes
 
     t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -361,9 +415,21 @@ def main():
     # launch gaps that per-call events in an eager pass include.
     roof, per_kernel = None, None
     ops.RECORD["on"], ops.RECORD["calls"] = True, []
+    ops.PROFILE["on"], ops.PROFILE["events"] = world > 1, []
     trainer._run_eager()  # on every rank: the step contains the three collectives
     torch.cuda.synchronize()
     ops.RECORD["on"] = False
+    ops.PROFILE["on"] = False
+    # exchange kernels wait for their peers, so they cannot be replayed on one rank: they are timed in place (CUDA events
+    # around each call of the eager pass; the time includes waiting for the slowest rank = the exposed exchange time)
+    exchange = {}
+    for name, tag, ea, eb in ops.PROFILE["events"]:
+        if name.startswith(("mca_dp_", "mca_p2p_", "mca_xgpu_barrier", "mca_contrastive_")):
+            d = exchange.setdefault(name, {"ms_total_per_step": 0.0, "launches_per_step": 0})
+            d["ms_total_per_step"] += ea.elapsed_time(eb)
+            d["launches_per_step"] += 1
+    for d in exchange.values():
+        d["us_avg"] = d["ms_total_per_step"] / d["launches_per_step"] * 1e3
     if rank == 0:
         calls = ops.RECORD["calls"]
         groups = {}
@@ -390,6 +456,8 @@ def main():
             torch.cuda.synchronize()
             ms = a0.elapsed_time(a1) / (reps * len(lst))
             per_kernel[key] = {"ms_total_per_step": ms * len(lst), "launches_per_step": len(lst), "us_avg": ms * 1e3}
+        for k, v in exchange.items():
+            per_kernel[k + " (in place)"] = v
         per_kernel = dict(sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_total_per_step"]))
         if os.environ.get("MCA_BENCH_TABLE"):
             os.makedirs(os.path.dirname(os.environ["MCA_BENCH_TABLE"]) or ".", exist_ok=True)
@@ -397,7 +465,9 @@ def main():
                 json.dump(per_kernel, f, indent=1)
         peaks = read_peaks()
         fl = algorithmic_flops(eng.plan, B, eng.H, eng.depth, eng.I)
-        top = next(iter(per_kernel))
+        live_pairs = live_allowed_pairs(eng.plan, host_batch)  # = plan.allowed_pairs for the unpadded workload
+        fl["attn_layer_fwd"] = live_pairs * B * eng.H * 4 * 64
+        top = next(k for k in per_kernel if not k.endswith("(in place)"))
         tname = top.split(":")[0]
         flops_map = {"mca_attn_bwd": 2 * fl["attn_layer_fwd"], "mca_attn_fwd": fl["attn_layer_fwd"]}
         if tname == "mca_gemm_bf16":
@@ -408,15 +478,20 @@ def main():
             f = flops_map[tname]
             dur = per_kernel[top]["us_avg"] * 1e-6
             ach = f / dur / 1e12
-            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"],
+            # the kernel is timed ALONE (back-to-back launches of this one kernel, a few ms): the burst cuBLAS figure is the
+            # denominator; the fraction of the sustained figure (what a seconds-long loop under the power cap reaches) is
+            # stated beside it
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops"], "frac_of_sustained_peak": ach / peaks["bf16_tflops_sustained"],
+                    "live_allowed_pairs_per_sample_head": live_pairs, "static_allowed_pairs": eng.plan.allowed_pairs,
                     "traffic": ncu_traffic(tname) if args.config == "CMU_config1" else None,  # captured on that workload
                     "algorithmic_flops_per_launch": f, "avg_launch_us": per_kernel[top]["us_avg"],
                     "launches_per_step": per_kernel[top]["launches_per_step"],
-                    "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
+                    "peak_source": peaks["source"] + " (bf16_tflops, burst: kernel timed in isolation)",
                     "how": "CUDA events around back-to-back device launches of every call of this kernel in one step "
                            "(recorded from an eager pass of the same step, same process); attention FLOPs count only "
-                           "mask-allowed (q,k) pairs, the launch also covers its memset / prep / cast helpers"}
+                           "mask-allowed (q,k) pairs whose key is live in this batch; the launch also covers its memset / prep / "
+                           "cast helpers"}
         else:
             roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
                     "traffic": None, "avg_launch_us": per_kernel[top]["us_avg"], "peak_source": peaks["source"]}
@@ -430,16 +505,43 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        bs, n_timed = 4, 2
-        step = cpu_training_step_fn(args.config, bs)
+        bs, n_timed = B, 2
+        step = cpu_training_step_fn(args.config, bs, variant=args.variant)
         step()  # warm-up (allocator, thread pool)
         t0 = time.perf_counter()
         for _ in range(n_timed):
             step()
         dt = (time.perf_counter() - t0) / n_timed
         cpu_base = {"value": bs / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{n_timed} timed CPU training steps (fwd+bwd+clip+AdamW, fp32, after 1 warm-up) on {bs} samples of the "
-                              f"same shape, oracle/mca_oracle.py"}
+                    "sample": f"{n_timed} timed CPU training steps (fwd+bwd+clip+AdamW, fp32, after 1 warm-up) on the same {bs}-sample "
+                              f"batch (same config, same batch size as the B200 arm), oracle/mca_oracle.py"}
+    # ---- eager fp32 baseline on the SAME B200 (SURVEY.md §6 / §8d "the real bar"): the oracle port (= the reference's
+    # op sequence: cuBLAS fp32 SIMT GEMMs with TF32 off, materialised [B,h,N,N] scores, ATen softmax / layer_norm) on cuda
+    eager_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            del trainer
+            torch.cuda.empty_cache()
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            step = cpu_training_step_fn(args.config, B, device="cuda", variant=args.variant)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_g = 5
+            g0.record()
+            for _ in range(n_g):
+                step()
+            g1.record()
+            torch.cuda.synchronize()
+            ms = g0.elapsed_time(g1) / n_g
+            eager_gpu = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f32 (TF32 off, the reference default)",
+                         "kind": "port", "sample": f"{n_g} timed steps after 2 warm-up, same {B}-sample batch, torch eager on cuda:0 "
+                                                   "(oracle/mca_oracle.py + torch autograd + clip + AdamW)",
+                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+        except Exception as exc:  # an out-of-memory eager baseline must not lose the measured line
+            eager_gpu = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
     if rank == 0:
         value = world * B * args.steps / (ms_dev * 1e-3)
@@ -448,27 +550,25 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": (f"{args.config} EAO training step, B=8 per GPU ({eng.plan.n_mod} modalities, {eng.R} passes "
-                                    f"stacked block-diagonally -> N={eng.N} tokens per sample, d=512, {eng.depth} layers, mean "
-                                    f"pooling, {eng.plan.n_pairs} InfoNCE pairs), variant={args.variant}") if eng.eao else
-                                   (f"{args.config} MCA training step, B=8 per GPU (COVAREP 1500x74, FACET 450x35, OpenFace 450x713, "
-                                    f"GloVe 50x300, 88 fusion tokens -> N=2538, d=512, 5 layers, {eng.plan.n_pairs} InfoNCE pairs), "
-                                    f"variant={args.variant}"),
+            "config": {"workload": workload_string(args.config, args.variant),
                        "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graphs": not args.no_graphs,
                        "dp_exchange": ("none" if world == 1 else ("peer memory (push/pull kernels + flag barriers, one graph)"
                                                                  if eng._p2p is not None else "nccl")),
                        "l2": "per-step working set (~2 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "precision": "bf16 tensor-core operands, fp32 accumulate, fp32 master weights/residual stream/LN/softmax/loss"},
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": trainer.h2d_bytes, "d2h_bytes_per_step": 16,
-                    "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "note": "every step copies its batch from PINNED host buffers (a copy stream, one step ahead) and reads its "
+                            "loss summary back to pinned host memory inside the timed region; the pageable -> pinned memcpy a "
+                            "DataLoader worker would do is outside it"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cpu_base, "final_loss": final_loss,
-            "per_kernel_ms_per_step": {k: round(v["ms_total_per_step"], 4) for k, v in list(per_kernel.items())[:12]} if per_kernel else None,
+            "roofline": roof, "cpu_baseline": cpu_base, "eager_gpu_baseline": eager_gpu, "final_loss": final_loss,
+            "per_kernel_ms_per_step": {k: round(v["ms_total_per_step"], 4) for k, v in list(per_kernel.items())[:16]} if per_kernel else None,
         }
         print(json.dumps(line), flush=True)
-    eng.check_p2p()  # raises if a peer GPU missed one of the flag barriers (would invalidate the number)
     if world > 1:
+        eng.check_p2p()  # raises if a peer GPU missed one of the flag barriers (would invalidate the number)
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 

@@ -138,7 +138,7 @@ def tabular_encode(sd: dict, prefix: str, data: dict, max_value: float, padding_
     # index = arange(n): every row, in order; the padding_idx row (-1 -> n-1) receives no gradient
     n_rows = emb.shape[0]
     pi = int(padding_value) % n_rows
-    keep = torch.ones(n_rows, 1, dtype=emb.dtype)
+    keep = torch.ones(n_rows, 1, dtype=emb.dtype, device=emb.device)
     keep[pi] = 0.0
     x_t = emb * keep + (emb * (1.0 - keep)).detach()
     v = values.unsqueeze(-1)
@@ -161,7 +161,7 @@ def _lookup_with_renorm(emb: torch.Tensor, idx: torch.Tensor, padding_idx: int, 
         if renorm_in_place:
             emb[used] = emb[used] * scale
     n_rows = emb.shape[0]
-    keep = torch.ones(n_rows, 1, dtype=emb.dtype)
+    keep = torch.ones(n_rows, 1, dtype=emb.dtype, device=emb.device)
     keep[padding_idx % n_rows] = 0.0
     table = emb * keep + (emb * (1.0 - keep)).detach()
     return table[idx]
@@ -425,7 +425,7 @@ def mean_token_pool(x, key_padding_mask):
     rows = []
     for i in range(x.shape[0]):
         v = x[i, ~key_padding_mask[i], :]
-        rows.append(torch.zeros(x.shape[2], dtype=x.dtype) if v.shape[0] == 0 else v.mean(dim=0))
+        rows.append(torch.zeros(x.shape[2], dtype=x.dtype, device=x.device) if v.shape[0] == 0 else v.mean(dim=0))
     out = torch.stack(rows).unsqueeze(1)
     if out.isnan().any():
         raise Exception(f"NaN in output from Mean Pooling {int(out.isnan().sum())}, could be from any place before this")
