@@ -222,6 +222,24 @@ int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8_t* present
                                  int n_pairs, float* logit_scale, int B, int GB, int R, int d, int n_mod, int rank,
                                  const float* w, float* dpooled_all, float* dscale, void* stream);
 
+/* Free-standing calls of the reference surface (not on the fused MCA.forward path, which never materialises logits or
+ * attention probabilities).  Functional contrastive_loss_with_temperature(...) -> ContrastiveLossOutput
+ * (utils/contrastive_loss_with_temperature.py:40-108): logits[i,j] = exp(*logit_scale) * <a_i, b_all_j> (:71,82-88);
+ * F.cross_entropy rows with label_smoothing (cross_entropy_kwargs, :94-100): row_loss / row_lse [rows]; backward:
+ * dlogits[rows,cols] = g_row[i] * dCE/dz * exp(*logit_scale) (logit_scale may be NULL: factor 1),
+ * *dscale += sum dCE/dz * z (caller zeroes it; may be NULL). */
+int mca_scaled_logits_f32(const float* a, const float* b_all, const float* logit_scale, int n_a, int n_b, int d,
+                          float* logits, void* stream);
+int mca_cross_entropy_fwd(const float* logits, long long ld, const long long* labels, int rows, int cols,
+                          float label_smoothing, float* row_loss, float* row_lse, void* stream);
+int mca_cross_entropy_bwd(const float* logits, long long ld, const long long* labels, int rows, int cols,
+                          float label_smoothing, const float* row_lse, const float* g_row, const float* logit_scale,
+                          float* dlogits, float* dscale, void* stream);
+/* Attention(..., return_attn=True) (model.py:96,102-103): probs [B,H,N,N] fp32 recomputed from the saved lse of
+ * mca_attn_fwd; fully masked rows (lse = +inf) are uniform over all N keys (quirk Q4). */
+int mca_attn_probs(const void* qkv, const float* lse, const uint32_t* rowbits, const uint8_t* keygrp,
+                   const uint8_t* padding, int B, int N, int H, float* probs, void* stream);
+
 /* Peer-memory exchange of the pooled block for data parallelism inside one NVLink/NVSwitch domain (replaces the
  * all_gather / reduce_scatter of utils/distributed.py:23-56 and torch.distributed.nn.functional.all_gather's backward).
  * The gathered [GB,R,d] buffers live in P2P-mapped symmetric memory, one per rank, addressable by all ranks:

@@ -1,6 +1,6 @@
 """Modality encoders with the reference's constructor surface and state_dict names (encoders.py:17-283).
 
-The modules only *hold* parameters/buffers (so checkpoints of the reference load unchanged); the arithmetic of all five
+The modules hold parameters/buffers (so checkpoints of the reference load unchanged); the arithmetic of all five
 encoder types — EmbeddedSequenceEncoder (CMU), TabularEncoder (TCGA), and SequenceEncoder / SparseTabularEncoder /
 PatchEncoder (no shipped config uses them) — runs in the fused CUDA path driven by
 mca_paper_b200.engine.Engine.encode(), which writes tokens straight into the packed [B, N, 512] buffer.
@@ -57,10 +57,12 @@ class _EncoderBase(nn.Module):
         raise NotImplementedError
 
     def forward(self, batch):
-        raise NotImplementedError(
-            f"{type(self).__name__} holds parameters only: its arithmetic runs inside the fused MCA path "
-            "(mca_paper_b200.engine.Engine.encode, called by MCA.forward), which writes the tokens straight into the "
-            "packed [B, N, 512] buffer")
+        """`(tokens [B, L, 512], attention_mask)` like the reference encoders.  Inside MCA.forward the engine runs the
+        same kernels and writes the tokens straight into the packed [B, N, 512] buffer; this free-standing call goes
+        through an encoders-only engine built around the module (standalone.encoder_forward)."""
+        from .standalone import encoder_forward
+
+        return encoder_forward(self, batch)
 
 
 class EmbeddedSequenceEncoder(_EncoderBase):

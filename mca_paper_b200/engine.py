@@ -34,8 +34,10 @@ def _round_up(x, m):
 
 
 class Engine:
-    def __init__(self, model, plan: StaticPlan, depth: int, heads: int, ff_inner: int, batch_size: int):
+    def __init__(self, model, plan: StaticPlan, depth: int, heads: int, ff_inner: int, batch_size: int,
+                 trunk: bool = True):
         self.model = model
+        self.trunk = bool(trunk)   # False: encoders only (free-standing encoder(batch) calls, standalone.py)
         self.plan = plan
         self.depth, self.H, self.I = depth, heads, ff_inner
         if heads * DH != D:
@@ -168,7 +170,7 @@ class Engine:
             add_matrix(p + "out", (D, D), [(p + "attn.to_out.weight", D, D, 0, 0, 0, 1.0)], M)
             add_matrix(p + "ff1", (2 * IP, D), [(p + "ff.feedforward.0.weight", 2 * I, D, 0, 1, I, 1.0)], M)
             add_matrix(p + "ff2", (D, IP), [(p + "ff.feedforward.2.weight", D, I, 0, 0, 0, 1.0)], M)
-        if not self.eao:
+        if not self.eao and self.trunk:
             add_matrix("attn_pool.kv", (2 * D, D), [("attn_pool.to_kv.weight", 2 * D, D, 0, 0, 0, 1.0)], M)
         self.enc_kpad = {}
         for name, enc in zip(self.plan.names, self.model.encoder_specs):
@@ -236,7 +238,7 @@ class Engine:
         if self.eao:
             ws["pool_cnt"] = f32(B, R)
             ws["pool_scratch"] = f32(int(ops.fn("mca_mean_pool_scratch_floats")(B, R)))
-        else:
+        elif self.trunk:
             ws["kvp"] = b16(M, 2 * D)
             ws["qp"], ws["probs"], ws["fm"] = f32(R, D), f32(B, H, R, N), u8(B, R)
             ws["po"] = f32(B, R, D)
@@ -275,7 +277,7 @@ class Engine:
         ws["du"], ws["dattn"], ws["dqkv"] = b16(M, 2 * IP), b16(M, D), b16(M, 3 * D)
         ws["dq_acc"], ws["delta"], ws["ucorr"] = f32(M, D), f32(B, H, N), f32(B, D)
         ws["dxf"] = f32(M, D)
-        if not self.eao:
+        if not self.eao and self.trunk:
             ws["dkvp"] = b16(M, 2 * D)
             ws["pool_ds"], ws["dqp"], ws["dpo"] = f32(B, H, R, N), f32(R, D), f32(B, R, D)
         self.ws = ws

@@ -55,10 +55,12 @@ class LayerNorm(nn.Module):
 
 
 class GEGLU(nn.Module):
-    """Placeholder that keeps `feedforward.{0,2}` state_dict indices (model.py:35-38); fused into the FF1 epilogue."""
+    """Keeps the `feedforward.{0,2}` state_dict indices (model.py:35-38).  Inside FeedForward / MCA it is fused into
+    the FF1 GEMM epilogue; there is no stand-alone GEGLU kernel (the activation never exists as a separate pass)."""
 
     def forward(self, x):
-        raise NotImplementedError("GEGLU is fused into the feed-forward GEMM epilogue; call FeedForward instead")
+        raise NotImplementedError("GEGLU is fused into the feed-forward GEMM epilogue (mca_gemm_bf16, MCA_EPI_GEGLU); "
+                                  "call FeedForward, which runs Linear -> GEGLU -> Linear on the kernels")
 
 
 class FeedForward(nn.Module):
@@ -86,9 +88,12 @@ class Attention(nn.Module):
         self.to_out = nn.Linear(inner_dim, dim, bias=False)
 
     def forward(self, x, context=None, attn_mask=None, key_padding_mask=None, return_attn=False):
-        raise NotImplementedError(
-            "Attention runs inside the fused MCA path (block-sparse tcgen05 kernel driven by the model's static "
-            "schedule); a free-standing call with an arbitrary dense mask is not part of the hot path")
+        """model.py:73-105 as a free-standing call (inside MCA.forward the engine drives the same kernels from the
+        model's static schedule): standalone.attention derives the block-sparse schedule from `attn_mask`."""
+        from .standalone import attention
+
+        return attention(self, x, context=context, attn_mask=attn_mask, key_padding_mask=key_padding_mask,
+                         return_attn=return_attn)
 
 
 class MCALayer(nn.Module):
@@ -101,6 +106,14 @@ class MCALayer(nn.Module):
         self.num_heads = heads
         self.ff = FeedForward(dim=dim, mult=ff_mult)
         self.norm = LayerNorm(dim)
+
+    def forward(self, batch, attn_mask=None, padding_mask=None):
+        """model.py:117-122 as a free-standing call (quirk Q1: one shared norm, residuals from the normed tensor)."""
+        batch = self.norm(batch)
+        batch = self.attn(batch, attn_mask=attn_mask, key_padding_mask=padding_mask) + batch
+        batch = self.norm(batch)
+        batch = self.ff(batch) + batch
+        return batch
 
 
 class MCAPretrainingLoss(nn.Module):

@@ -72,6 +72,10 @@ _SIGS = {
     "mca_tabular_fwd": [VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_tabular_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, F32, F32, I32, I64, VP],
     "mca_embedding_renorm": [VP, I32, I32, F32, VP],
+    "mca_scaled_logits_f32": [VP, VP, VP, I32, I32, I32, VP, VP],
+    "mca_cross_entropy_fwd": [VP, I64, VP, I32, I32, F32, VP, VP, VP],
+    "mca_cross_entropy_bwd": [VP, I64, VP, I32, I32, F32, VP, VP, VP, VP, VP, VP],
+    "mca_attn_probs": [VP, VP, VP, VP, VP, I32, I32, I32, VP, VP],
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS.keys())

@@ -281,3 +281,57 @@ class EAOPlan(StaticPlan):
 
     def _segments(self):
         return list(zip(self.block_offsets, self.mask_lengths))
+
+
+class MaskPlan(StaticPlan):
+    """Schedule of a free-standing `Attention(x, attn_mask=...)` call (model.py:73-105, standalone.attention) derived
+    from the dense boolean mask itself (True = may not attend, model.py:90-91): keys whose mask COLUMNS are identical
+    form one key group, a query row's bits say which groups it sees.  Every mask the reference builds is of this form
+    with at most 23 groups; an arbitrary mask is accepted as long as it has at most 32 distinct
+    columns.  Tiles follow the runs of equal key group (runs shorter than a tile are merged into mixed tiles, which the
+    kernels mask per key)."""
+
+    def __init__(self, attn_mask, n: int):
+        self.eao = False
+        self.N = int(n)
+        if attn_mask is None:
+            attn_mask = np.zeros((self.N, self.N), dtype=bool)
+        attn_mask = np.ascontiguousarray(attn_mask, dtype=bool)
+        if attn_mask.shape != (self.N, self.N):
+            raise AssertionError(f"attn_mask {attn_mask.shape} != {(self.N, self.N)}")
+        allowed = ~attn_mask
+        cols, first, inv = np.unique(allowed.T, axis=0, return_index=True, return_inverse=True)
+        inv = np.asarray(inv).reshape(-1)
+        # number the groups in order of first appearance (keeps the reference's modality order for its own masks)
+        order = np.argsort(first, kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(len(order))
+        keygrp = rank[inv]
+        self.n_groups = int(len(cols))
+        if self.n_groups > 32:
+            raise NotImplementedError(f"attn_mask has {self.n_groups} distinct key columns; the block-sparse attention "
+                                      "kernels support masks with at most 32 key groups")
+        self.keygrp = keygrp.astype(np.uint8)
+        rep = np.asarray(first)[order]                         # one representative key per group
+        bits = (allowed[:, rep].astype(np.uint64) << np.arange(self.n_groups, dtype=np.uint64)[None, :]).sum(axis=1)
+        self.rowbits = bits.astype(np.uint32)
+        self.attn_mask = ~(((self.rowbits[:, None] >> self.keygrp[None, :].astype(np.uint32)) & 1).astype(bool))
+        if not np.array_equal(self.attn_mask, attn_mask):
+            raise AssertionError("internal error: key-group factorisation does not reproduce attn_mask")
+        # segments: maximal runs of one key group; neighbouring runs shorter than a tile merge into one mixed segment
+        runs, s = [], 0
+        for i in range(1, self.N + 1):
+            if i == self.N or self.keygrp[i] != self.keygrp[s]:
+                runs.append((s, i - s))
+                s = i
+        segs = []
+        for o, ln in runs:
+            if segs and ln < TILE and segs[-1][2]:
+                segs[-1] = (segs[-1][0], segs[-1][1] + ln, True)
+            else:
+                segs.append((o, ln, ln < TILE))
+        self._segs = [(o, ln) for o, ln, _ in segs]
+        self._build_tiles()
+
+    def _segments(self):
+        return self._segs

@@ -352,3 +352,37 @@ def test_named_configs_equal_the_reference_yaml(name):
                 assert dict(a[m]) == dict(b[m]), (m, a[m], b[m])
         else:
             assert (list(a) if isinstance(a, (list, tuple)) else a) == (list(b) if isinstance(b, (list, tuple)) else b), k
+
+
+def test_mask_plan_factorises_dense_masks_into_key_groups():
+    """plan.MaskPlan (free-standing Attention calls): key groups / row bits reproduce the dense mask bit for bit, equal
+    the model's own tables on the reference masks, and the tile schedule covers exactly the tiles holding allowed pairs."""
+    import numpy as np
+    from mca_paper_b200.plan import MaskPlan, StaticPlan, TILE
+
+    for kind, kw in (("cmu", dict(fcl=True)), ("cmu", dict(zorro=True, fcl=False)), ("tcga", dict(fcl=True))):
+        k = C.get_model_config(C.tiny_config(kind, **kw))
+        sp = StaticPlan(k["encoder_configs"], k["num_fusion_tokens"], list(k["fusion_combos"]), k["fcl"],
+                        k.get("zorro", False), k.get("no_fusion", False), False, False)
+        mp = MaskPlan(sp.attn_mask, sp.N)
+        assert np.array_equal(mp.attn_mask, sp.attn_mask)
+        assert np.array_equal(mp.keygrp, sp.keygrp) and np.array_equal(mp.rowbits, sp.rowbits)
+    rng = np.random.default_rng(3)
+    for n, ng in ((1, 1), (129, 2), (700, 6), (1000, 32)):
+        grp = np.sort(rng.integers(0, ng, size=n))
+        vis = rng.random((ng, ng)) < 0.4
+        mask = ~vis[grp][:, grp]
+        mp = MaskPlan(mask, n)
+        assert np.array_equal(mp.attn_mask, mask) and mp.n_groups <= ng + 1
+        covered = np.zeros((n, n), dtype=bool)
+        assert int(mp.tiles[:, 1].sum()) == n and (mp.tiles[:, 1] <= TILE).all()
+        for qs, ql, off, cnt in mp.q_tiles:
+            for t, flag in mp.kt_list[off:off + cnt]:
+                ks, kl = mp.tiles[t]
+                blk = ~mask[qs:qs + ql, ks:ks + kl]
+                assert blk.any() and (flag == 0) == bool(blk.all())
+                covered[qs:qs + ql, ks:ks + kl] = True
+        assert not (~mask & ~covered).any()
+    with pytest.raises(NotImplementedError):
+        MaskPlan(rng.random((64, 64)) < 0.5, 64)
+    assert MaskPlan(None, 300).n_groups == 1
