@@ -320,6 +320,9 @@ def main():
     ap.add_argument("--variant", default="full")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="for ncu --profile-from-start off: warm up, then bracket exactly ONE eager training step with "
+                         "cudaProfilerStart/Stop and exit (no timing, no JSON line: a number taken under a profiler is not a bench value)")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="infer = SURVEY.md §8d config 5: eval() forward + losses of infer_accel_gpu.py:97-111, replicas only")
     args = ap.parse_args()
@@ -365,6 +368,12 @@ def main():
         trainer.stage(host_batch)
         trainer.step_staged()
     torch.cuda.synchronize()
+    if args.profile_step:
+        torch.cuda.cudart().cudaProfilerStart()
+        trainer._run_eager()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     loss_pinned = torch.empty(4, pin_memory=True)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None

@@ -1,39 +1,204 @@
-"""Data-parallel sanity check (run under torchrun, one rank per GPU): replicas stay bit-identical after optimiser
-steps on rank-specific data, the gathered-loss path runs, and rank 0's loss equals the single-process emulation of
-the same global batch computed with the CPU oracle on the pooled embeddings."""
-import os, sys
+"""Data-parallel check against the ORACLE (run under torchrun, one rank per GPU).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 \
+        scripts/gpu_dp_check.py [tiny|tiny_z|full|full_z]
+
+Every rank restates the whole G-rank step with `oracle.mca_forward_ranks` (fp32, TF32 off, on its own GPU): rank s scores
+its rows against the gathered columns of all ranks with labels B*s + arange(B)
+(utils/contrastive_loss_with_temperature.py:26-31,71-100), the all-gather back-propagates (reduce-scatter SUM,
+utils/distributed.py:23-56) and DDP averages the parameter gradients over the ranks (train_accel_gpu.py:93,115):
+    grad_ref = d(sum_s loss_s) / d theta  / G.
+Checked on every rank, for the peer-memory exchange kernels (and the NCCL form under MCA_P2P=0):
+  1. the rank's loss and its returned embeddings against the oracle's rank-s outputs (2e-2, bf16 operands);
+  2. the REDUCED gradient of the rank's optimiser shard (mca_dp_reduce_shard output x 1/G) against grad_ref, per
+     parameter tensor that overlaps the shard (5e-2 worst, 2e-2 median, as in tests/test_gpu_fullsize.py) — a wrong 1/G,
+     a mis-addressed shard or a dropped peer fails here;
+  3. the global gradient norm the clip uses against ||grad_ref||;
+  4. the parameters after the sharded clip + AdamW + parameter push against `oracle.clip_adamw_step` applied to the
+     product's own reduced gradient (all-gathered with NCCL for the check): 1e-6, on the WHOLE flat buffer, so every
+     peer's pushed shard is covered;
+  5. replicas bit-identical; a second step through the captured graph reproduces the oracle's second-step loss;
+  6. the peer-memory loss exchange against the NCCL all_gather / reduce_scatter form on identical inputs;
+  7. checkpoint save -> two more steps -> load -> the next step reproduces the uninterrupted run.
+"""
+import os
+import sys
+
 import torch
 import torch.distributed as dist
+
 sys.path.insert(0, ".")
-from mca_paper_b200 import config as C, synthetic as S
-from mca_paper_b200.model import MCA
-from mca_paper_b200.trainer import Trainer
+from mca_paper_b200 import config as C, synthetic as S  # noqa: E402
+from mca_paper_b200.model import MCA  # noqa: E402
+from mca_paper_b200.trainer import Trainer  # noqa: E402
+from oracle import mca_oracle as O  # noqa: E402  (checker only)
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-cfg = C.named_config(sys.argv[1] if len(sys.argv) > 1 else "CMU_config1_z")
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+mode = sys.argv[1] if len(sys.argv) > 1 else "tiny"
+zorro = mode.endswith("_z")
+if mode.startswith("full"):
+    cfg = C.named_config("CMU_config1_z" if zorro else "CMU_config1")
+else:  # CMU_config1's full parameter set (d = 512, 5 layers, same encoders) on ~300 tokens per sample
+    cfg = C.tiny_config("cmu", zorro=zorro, fcl=not zorro, layers=5)
 kw = C.get_model_config(cfg)
+LR, CLIP = 1e-4, 2.0
+
+
+def say(msg):
+    print(f"[rank {rank}/{world}] {msg}", flush=True)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def to_dev(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.to(dev)
+    if isinstance(obj, dict):
+        return {k: to_dev(v) for k, v in obj.items()}
+    return obj
+
+
+# ---- model: well-conditioned initialisation (tests/test_gpu_fullsize.py WELL) so that gradients are comparable
 torch.manual_seed(int(cfg["seed"]))
-model = MCA(**kw).to(dev)
-tr = Trainer(model, lr=1e-4, clip=2.0, schedule="cosine", warmup_steps=10, total_steps=1000)
+model = MCA(**kw)
+with torch.no_grad():
+    model.return_tokens.mul_(0.05)
+    model.loss.loss_fn.logit_scale.fill_(1.0)
+sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+names = [k for k, _ in model.named_parameters()]
+batches = [S.make_batch(cfg, seed=1 + s, variant="dropout_ragged") for s in range(world)]
+
+# ---- oracle: the G-rank step, two optimiser steps
+sdg = {k: v.clone().to(dev) for k, v in sd0.items()}
+o_params = [sdg[k].requires_grad_(True) for k in names]
+o_m = [torch.zeros_like(p) for p in o_params]
+o_v = [torch.zeros_like(p) for p in o_params]
+tables = to_dev(O.static_tables(kw))
+o_batches = [to_dev(b) for b in batches]
+o_steps = []
+for step in (1, 2):
+    for p in o_params:
+        p.grad = None
+    outs = O.mca_forward_ranks(sdg, kw, o_batches, tables=tables)
+    sum(o["loss"] for o in outs).backward()
+    grads = [(p.grad if p.grad is not None else torch.zeros_like(p)) / world for p in o_params]
+    rec = {"loss": [float(o["loss"]) for o in outs], "grads": {k: g.detach().clone() for k, g in zip(names, grads)},
+           "emb": {k: v.detach().clone() for k, v in outs[rank].items() if isinstance(v, torch.Tensor) and v.dim() == 2}}
+    with torch.no_grad():
+        rec["norm"] = float(O.clip_adamw_step(o_params, grads, o_m, o_v, step, lr=LR, max_norm=CLIP))
+    o_steps.append(rec)
+del outs
+torch.cuda.empty_cache()
+
+# ---- product: step 1 in eager segments so that the intermediate buffers can be inspected
+model = model.to(dev)
+tr = Trainer(model, lr=LR, clip=CLIP, schedule="constant", use_graphs=True)
 eng = tr.eng
-batch = S.make_batch(cfg, seed=1 + rank, variant="dropout_ragged")
-losses = []
-for step in range(3):
-    s = tr.step(batch)
-    losses.append(float(s[0]))
+exch = "p2p (symmetric memory)" if eng._p2p is not None else "nccl"
+tr.stage(batches[rank])
+tr._seg_forward()
+tr._seg_loss()
+tr._seg_backward()
 torch.cuda.synchronize()
-# replicas identical?
-# (the peer-memory optimiser keeps AdamW moments only for the rank's own shard: compare parameters there)
-chk = torch.stack([eng.flat.double().sum(), eng.flat.double().abs().sum(),
-                   eng.exp_avg.double().abs().sum() if eng._p2p is None else eng.flat.double().pow(2).sum()])
-allc = [torch.zeros_like(chk) for _ in range(world)]
-dist.all_gather(allc, chk)
-same = all(torch.equal(allc[0], c) for c in allc)
+# 1. loss + embeddings of this rank
+loss1 = float(eng.ws["summary"][0])
+want = o_steps[0]["loss"][rank]
+assert abs(loss1 - want) < 2e-2 * abs(want), (loss1, want)
+worst_emb = 0.0
+for key, row in eng.plan.output_rows:
+    if key in o_steps[0]["emb"]:
+        worst_emb = max(worst_emb, rel(eng.ws["pooled"][:, row, :], o_steps[0]["emb"][key]))
+assert worst_emb < 2e-2, worst_emb
+say(f"{mode} [{exch}] step-1 loss {loss1:.6f} vs oracle {want:.6f}; worst embedding rel err {worst_emb:.2e}")
+
+# 2./3./4. the optimiser step, with the reduced gradient captured between its kernels
+flat_before = eng.flat.detach().clone()
+flat_ref_grad = torch.zeros_like(eng.flat_grad)
+for name, p in eng._param_list():
+    o = eng.offs[name]
+    flat_ref_grad[o:o + p.numel()] = o_steps[0]["grads"][name].reshape(-1)
+if eng._p2p is not None:
+    import ctypes
+    from mca_paper_b200.ops import P, S as STREAM, call
+    p2 = eng._p2p
+    off, n = eng.shard()
+    eng.xgpu_barrier()
+    call("mca_dp_reduce_shard", P(p2["grad_peers"]), P(eng.flat_grad), off, n, world, P(p2["sumsq_local"]), STREAM())
+    torch.cuda.synchronize()
+    mine = (eng.flat_grad[off:off + n] / world).clone()          # the reduced mean gradient of this rank's shard
+    eng.xgpu_barrier(payload=p2["sumsq_local"])
+    call("mca_dp_adamw_shard", P(p2["param_peers"]), world, rank, P(eng.flat_grad), P(eng.exp_avg), P(eng.exp_avg_sq), off, n,
+         P(p2["slots"]), P(eng.step_dev), P(eng.total_norm), 1.0 / world, ctypes.addressof(eng.adamw_cfg), STREAM())
+    eng.xgpu_barrier()
+    eng.pack_weights()
+    per = eng.shard_size(eng.n_flat, world)
+    pad = torch.zeros(per, device=dev)
+    pad[:n] = mine
+    full = torch.empty(per * world, device=dev)
+    dist.all_gather_into_tensor(full, pad)
+    red = full[:eng.n_flat]
+else:
+    off, n = 0, eng.n_flat
+    tr._seg_optim()
+    red = eng.flat_grad / world                                   # all_reduce(SUM) leaves the sum in place
+    mine = red
+torch.cuda.synchronize()
+errs = []
+for name, p in eng._param_list():
+    o = eng.offs[name]
+    a, b = max(o, off), min(o + p.numel(), off + n)
+    if a >= b or name == "loss.loss_fn.logit_scale":
+        continue
+    ref = flat_ref_grad[a:b]
+    if float(ref.abs().max()) == 0.0:
+        assert float(red[a:b].abs().max()) == 0.0, name
+        continue
+    errs.append((rel(red[a:b], ref), name))
+errs.sort(reverse=True)
+assert errs and errs[0][0] < 5e-2 and errs[len(errs) // 2][0] < 2e-2, errs[:4]
+whole = rel(red, flat_ref_grad)
+cos = float((red.double() @ flat_ref_grad.double()) / (red.double().norm() * flat_ref_grad.double().norm()))
+gnorm = float(eng.total_norm)
+assert abs(gnorm - o_steps[0]["norm"]) < 2e-2 * o_steps[0]["norm"], (gnorm, o_steps[0]["norm"])
+say(f"reduced gradient (shard [{off}, {off + n})): worst tensor {errs[0][0]:.2e} ({errs[0][1]}), median {errs[len(errs) // 2][0]:.2e}; "
+    f"whole flat gradient rel {whole:.2e}, cosine {cos:.6f}; clip norm {gnorm:.5f} vs oracle {o_steps[0]['norm']:.5f}")
+# 4. parameters == oracle clip + AdamW on the product's own reduced gradient, over the WHOLE flat buffer
+chk_p = [flat_before[eng.offs[nm]:eng.offs[nm] + p.numel()].clone() for nm, p in eng._param_list()]
+chk_g = [red[eng.offs[nm]:eng.offs[nm] + p.numel()].clone() for nm, p in eng._param_list()]
+O.clip_adamw_step(chk_p, chk_g, [torch.zeros_like(x) for x in chk_p], [torch.zeros_like(x) for x in chk_p], 1, lr=LR, max_norm=CLIP)
+worst_p = max(rel(eng.flat[eng.offs[nm]:eng.offs[nm] + p.numel()], q) for (nm, p), q in zip(eng._param_list(), chk_p))
+assert worst_p < 1e-6, worst_p
+# ... and close to the oracle's own step-1 parameters (different gradient rounding: loose)
+worst_po = max(rel(eng.flat[eng.offs[nm]:eng.offs[nm] + p.numel()], q) for (nm, p), q in zip(eng._param_list(), o_params))
+say(f"parameters after step 1: vs oracle AdamW on the same gradient {worst_p:.2e} (bar 1e-6); vs the oracle's own step {worst_po:.2e}")
+assert worst_po < 1e-3, worst_po
+
+
+def replicas_identical():
+    chk = torch.stack([eng.flat.double().sum(), eng.flat.double().abs().sum(), eng.flat.double().pow(2).sum()])
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    return all(torch.equal(allc[0], c) for c in allc)
+
+
+assert replicas_identical(), "replicas diverged after step 1"
+# 5. second step through the captured graph
+loss2 = float(tr.step(batches[rank])[0])
+torch.cuda.synchronize()
+want2 = o_steps[1]["loss"][rank]
+assert abs(loss2 - want2) < 2e-2 * abs(want2), (loss2, want2)
+assert replicas_identical(), "replicas diverged after step 2"
+say(f"step-2 loss (graph replay) {loss2:.6f} vs oracle {want2:.6f}; replicas bit-identical")
 eng.check_p2p()
-# same weights, same batch: the peer-memory loss exchange against the NCCL all_gather / reduce_scatter form
+
+# 6. same weights, same batch: the peer-memory loss exchange against the NCCL all_gather / reduce_scatter form
 if eng._p2p is not None:
     pooled = eng.trunk_forward(tr._dev_batch)
     l_a = eng.loss_forward(pooled)[0].clone()
@@ -44,33 +209,26 @@ if eng._p2p is not None:
     eng._p2p = saved
     torch.cuda.synchronize()
     dl = (l_a - l_b).abs().nan_to_num().max().item()
-    dd = ((d_a - d_b).norm() / d_b.norm()).item()
-    print(f"rank {rank}: p2p vs nccl  max |dloss| {dl:.3e}  rel |d dpooled| {dd:.3e}  losses[:4] {l_a[:4].tolist()} / {l_b[:4].tolist()}", flush=True)
+    dd = rel(d_a, d_b)
+    say(f"p2p vs nccl loss exchange: max |dloss| {dl:.3e}, rel |d dpooled| {dd:.3e}")
     assert dl < 1e-4 and dd < 1e-5, "peer-memory loss path disagrees with the NCCL path"
-mode = "p2p (symmetric memory)" if eng._p2p is not None else "nccl all_gather/reduce_scatter"
-if rank == 0:
-    print(f"world {world} [{mode}]: losses rank0 {[f'{l:.6f}' for l in losses]}; replicas identical: {same}; "
-          f"param checksum {allc[0][1].item():.6f}", flush=True)
-    assert same, "replicas diverged"
-    assert all(l == l for l in losses), "NaN loss"
-# checkpoint under the sharded optimiser: save_state gathers the moment shards (collective), rank 0 writes accelerate's
-# directory layout; a perturbed trainer that loads it must reproduce the uninterrupted run's next step on every rank
-from mca_paper_b200 import checkpoint as K
-ckpt = "/tmp/mca_dp_ckpt"
+
+# 7. checkpoint under the sharded optimiser
+from mca_paper_b200 import checkpoint as K  # noqa: E402
+ckpt = f"/tmp/mca_dp_ckpt_{mode}"
 K.save_state(tr, ckpt)
 dist.barrier()
-s_next = float(tr.step(batch)[0])
-want = eng.flat.clone()
-tr.step(batch)                                   # move on, so that load_state has something to undo
-assert K.load_state(tr, ckpt) == 3
-assert abs(eng.lr_at(4) - 1e-4 * (3 * world) / 10.0) < 1e-10 or 3 * world >= 10   # scheduler walked `world` per step
-s_again = float(tr.step(batch)[0])
+s_next = float(tr.step(batches[rank])[0])
+want_flat = eng.flat.clone()
+tr.step(batches[rank])                           # move on, so that load_state has something to undo
+assert K.load_state(tr, ckpt) == 2
+s_again = float(tr.step(batches[rank])[0])
 torch.cuda.synchronize()
-rel = ((eng.flat - want).norm() / want.norm()).item()
-print(f"rank {rank}: resume loss {s_again:.6f} vs {s_next:.6f}, rel |dparams| {rel:.3e}", flush=True)
-assert abs(s_again - s_next) <= 2e-3 * abs(s_next) and rel < 1e-5, "resume from checkpoint differs"
+r = rel(eng.flat, want_flat)
+say(f"resume loss {s_again:.6f} vs {s_next:.6f}, rel |dparams| {r:.3e}")
+assert abs(s_again - s_next) <= 2e-3 * abs(s_next) and r < 1e-5, "resume from checkpoint differs"
 eng.check_p2p()
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
-    print("DP CHECK OK", flush=True)
+    print(f"DP CHECK OK ({mode}, world {world}, {exch})", flush=True)
