@@ -509,6 +509,31 @@ def main():
         step_flops = 3 * (eng.depth * (fl["linear_layer_fwd"] + fl["attn_layer_fwd"]))
         roof["step_algorithmic_tflops"] = step_flops / (ms_dev / args.steps * 1e-3) / 1e12
 
+    # ---- the fp32-parity forward mode of the same step (north_star's 1e-3 bar; Engine.set_precision), N = 1 only: eager
+    # launches (the captured graph holds the bf16 path), CUDA events around 5 steps after 2 warm-up
+    fp32_mode = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not kw.get("eao"):
+        try:
+            eng.set_precision("fp32")
+            for _ in range(2):
+                trainer._run_eager()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(5):
+                trainer._run_eager()
+            f1.record()
+            torch.cuda.synchronize()
+            ms = f0.elapsed_time(f1) / 5
+            fp32_mode = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                         "what": "same training step with the fp32-parity forward (3-term bf16 split products on the tcgen05 GEMM, "
+                                 "fp32 attention / GEGLU / pooling; loss and embeddings within 1e-3 of the fp32 reference: "
+                                 "tests/test_gpu_exact.py), regular bf16 backward; eager launches"}
+        except Exception as exc:
+            fp32_mode = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+        finally:
+            eng.set_precision("bf16")
+
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -572,7 +597,7 @@ def main():
                             "loss summary back to pinned host memory inside the timed region; the pageable -> pinned memcpy a "
                             "DataLoader worker would do is outside it"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cpu_base, "eager_gpu_baseline": eager_gpu, "final_loss": final_loss,
+            "roofline": roof, "cpu_baseline": cpu_base, "eager_gpu_baseline": eager_gpu, "fp32_parity_mode": fp32_mode, "final_loss": final_loss,
             "per_kernel_ms_per_step": {k: round(v["ms_total_per_step"], 4) for k, v in list(per_kernel.items())[:16]} if per_kernel else None,
         }
         print(json.dumps(line), flush=True)

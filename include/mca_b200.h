@@ -279,6 +279,17 @@ int mca_dp_adamw_shard(float* const* params_peers_dev, int world, int rank, cons
                        long long* step_dev, float* total_norm_out, float grad_scale, const mca_adamw_cfg* cfg_host,
                        void* stream);
 
+/* The same two kernels over the NVSwitch MULTICAST mapping of the symmetric flat buffers (NVLS): the gradient shard is read
+ * with multimem.ld_reduce (the switch returns the sum over all ranks: 1/G of the pull traffic) and the updated parameters are
+ * written with multimem.st (one store, replicated by the switch into every rank's buffer).  *_multicast = the multicast
+ * address of the flat gradient / parameter buffer (torch symmetric memory: handle.multicast_ptr + offset). */
+int mca_dp_reduce_shard_mc(const float* grads_multicast, float* grads_local, long long shard_off, long long shard_n, int world,
+                           double* sumsq_local, void* stream);
+int mca_dp_adamw_shard_mc(float* const* params_peers_dev, float* params_multicast, int world, int rank, const float* grads_local,
+                          float* exp_avg, float* exp_avg_sq, long long shard_off, long long shard_n, const double* sumsq_slots,
+                          long long* step_dev, float* total_norm_out, float grad_scale, const mca_adamw_cfg* cfg_host,
+                          void* stream);
+
 /* ---- Mean pooling of the EAO baseline: MeanTokenProjectionPool(token_types=None, projection=False), model.py:235-280 as
  * EAO.single_pass uses it (model.py:553-556,562-563).  x: bf16 [B, N, 512] final-normed tokens of all passes of a sample
  * laid back to back; padding [B, N] bytes (non-zero = padded key); pass_start [R + 1] token offsets; pooled [B, R, 512] =
@@ -311,6 +322,36 @@ int mca_uniformity(const float* x, long long M, int D, float t, int norm, float*
  * IndexError; the host wrapper checks). */
 int mca_retrieval_ranks(const float* emb, const float* targets, const long long* idx, long long M, long long T, int D,
                         float* inv_e, float* inv_t, float* own, long long* ranks, void* stream);
+
+/* ---- fp32-parity forward mode (csrc/exact.cu).  The reference computes in fp32 end to end (train_accel_gpu.py:21 default
+ * Accelerator(), no autocast; model.py:73-105), and north_star asks for loss / embeddings within 1e-3 of it.  Every dense
+ * contraction of the forward then runs as a 3-term bf16 split product on the SAME tensor-core GEMM: with x = hi + lo
+ * (hi = bf16(x), lo = bf16(x - hi)),  A W^T ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T  is one mca_gemm_bf16 over K' = 3K
+ * with operands [A_hi | A_hi | A_lo] and [W_hi | W_lo | W_hi].  These entry points produce those operands and the fp32
+ * pieces between the GEMMs; the attention core runs in fp32 on the CUDA cores (online softmax) and leaves the bf16 copies
+ * and the log-sum-exp the regular backward consumes.  Selected with Engine.set_precision("fp32") / MCA_PRECISION=fp32. */
+/* dst3 bf16 [rows, 3*kpad] <- src fp32 [rows, cols] (zero padded to kpad).  weight_layout 0: [hi|hi|lo], 1: [hi|lo|hi]. */
+int mca_x_split_f32(const float* src, long long ld_src, void* dst3, long long rows, int cols, int kpad, int weight_layout,
+                    void* stream);
+/* mca_pack_weights with every kernel-layout matrix written as [hi|lo|hi] (row stride 3*dst_ld, arena offsets x 3). */
+int mca_x_pack_weights_split(const float* params, void* arena3_bf16, const mca_pack_desc* descs_dev, int n_desc, void* stream);
+/* encoders.py:187-190 first LayerNorm (as mca_layernorm_in_fwd), output as the [hi|hi|lo] operand [rows, 3*kpad]. */
+int mca_x_layernorm_in_split(const float* x, const float* w, const float* b, const uint8_t* pad, void* y3, int width, int kpad,
+                             long long rows, void* stream);
+/* encoders.py:60-75 first stage (as mca_tabular_fwd), output as the [hi|hi|lo] operand [rows, 3*d]. */
+int mca_x_tabular_split(const float* values, const float* w1, const float* b1, void* h3, float max_value, int d,
+                        long long rows, void* stream);
+/* model.py:35-38 on the fp32 FF1 output u32 [M, 2*IP] ([64 value | 64 gate] per 128 columns): h3 = [hi|hi|lo] of
+ * h = x * gelu(g) [M, 3*IP]; h16 [M, IP] and u16 [M, 2*IP] = what MCA_EPI_GEGLU leaves for the backward. */
+int mca_x_geglu_f32(const float* u32, void* h3, void* h16, void* u16, long long M, int IP, void* stream);
+/* model.py:85-100 in fp32: qkv32 [B*N, 3*H*64] (q pre-scaled) -> out32 / out16 [B*N, H*64], lse [B,H,N]; allowed(q,k) =
+ * rowbits[q] >> keygrp[k] & 1 and padding[b,k] == 0; a row with no allowed live key gets vmean (mean of V over all N, Q4). */
+int mca_x_attn_fwd_f32(const float* qkv32, const uint32_t* rowbits, const uint8_t* keygrp, const uint8_t* padding, float* vmean,
+                       float* out32, void* out16, float* lse, int B, int N, int H, void* stream);
+/* mca_pool_attn_fwd on fp32 K | V rows. */
+int mca_x_pool_attn_fwd_f32(const float* qp, const float* kv32, const uint8_t* padding, const uint8_t* keygrp,
+                            const uint32_t* rowbits, float* probs, uint8_t* full_masked, float* out, int B, int H, int R, int N,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -115,17 +115,26 @@ clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
 //                     NVLink stores from inside the update kernel)
 // Every rank ends the step with bit-identical parameters.
 __global__ void __launch_bounds__(256)
-dp_reduce_shard_kernel(const float* const* __restrict__ grads_peers, float* __restrict__ grads_local, long long off,
-                       long long n, int world, double* __restrict__ sumsq_local) {
+dp_reduce_shard_kernel(const float* const* __restrict__ grads_peers, const float* grads_mc, float* __restrict__ grads_local,
+                       long long off, long long n, int world, double* __restrict__ sumsq_local) {
   __shared__ float red[8];
   float acc = 0.f;
   const long long n4 = n / 4;  // shards are multiples of 4 elements
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int g = 0; g < world; ++g) {
-      const float4 q = reinterpret_cast<const float4*>(grads_peers[g] + off)[i];
-      t.x += q.x, t.y += q.y, t.z += q.z, t.w += q.w;
+    if (grads_mc != nullptr) {
+      // NVSwitch in-fabric reduction: ONE load through the multicast address returns the sum over every rank's copy
+      // (1/G of the NVLink traffic of pulling G - 1 peers)
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                   : "l"(grads_mc + off + 4 * i)
+                   : "memory");
+    } else {
+      for (int g = 0; g < world; ++g) {
+        const float4 q = reinterpret_cast<const float4*>(grads_peers[g] + off)[i];
+        t.x += q.x, t.y += q.y, t.z += q.z, t.w += q.w;
+      }
     }
     reinterpret_cast<float4*>(grads_local + off)[i] = t;
     acc += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
@@ -142,7 +151,7 @@ dp_reduce_shard_kernel(const float* const* __restrict__ grads_peers, float* __re
 }
 
 __global__ void __launch_bounds__(256)
-dp_adamw_shard_kernel(float* const* __restrict__ params_peers, int world, int rank, const float* __restrict__ g,
+dp_adamw_shard_kernel(float* const* __restrict__ params_peers, float* params_mc, int world, int rank, const float* __restrict__ g,
                       float* __restrict__ m, float* __restrict__ v, long long off, long long n,
                       const double* __restrict__ sumsq_slots, const long long* __restrict__ step_ptr, float grad_scale,
                       mca_adamw_cfg c, float* __restrict__ total_norm_out) {
@@ -185,7 +194,14 @@ dp_adamw_shard_kernel(float* const* __restrict__ params_peers, int world, int ra
     }
     reinterpret_cast<float4*>(m + off)[i] = mq;
     reinterpret_cast<float4*>(v + off)[i] = vq;
-    for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(params_peers[r] + off)[i] = pq;
+    if (params_mc != nullptr) {
+      // one multicast store: the switch replicates it into every rank's parameter buffer (this rank's included)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(params_mc + off + 4 * i), "f"(pq.x),
+                   "f"(pq.y), "f"(pq.z), "f"(pq.w)
+                   : "memory");
+    } else {
+      for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(params_peers[r] + off)[i] = pq;
+    }
   }
 }
 
@@ -218,26 +234,62 @@ extern "C" int mca_clip_adamw_step(float* params, const float* grads, float* exp
   return check_launch();
 }
 
+static int dp_reduce_shard_impl(const float* const* grads_peers_dev, const float* grads_mc, float* grads_local,
+                               long long shard_off, long long shard_n, int world, double* sumsq_local, void* stream_);
+
 extern "C" int mca_dp_reduce_shard(const float* const* grads_peers_dev, float* grads_local, long long shard_off,
                                    long long shard_n, int world, double* sumsq_local, void* stream_) {
+  return dp_reduce_shard_impl(grads_peers_dev, nullptr, grads_local, shard_off, shard_n, world, sumsq_local, stream_);
+}
+
+extern "C" int mca_dp_reduce_shard_mc(const float* grads_multicast, float* grads_local, long long shard_off,
+                                      long long shard_n, int world, double* sumsq_local, void* stream_) {
+  if (grads_multicast == nullptr) return MCA_ERR_ARG;
+  return dp_reduce_shard_impl(nullptr, grads_multicast, grads_local, shard_off, shard_n, world, sumsq_local, stream_);
+}
+
+static int dp_reduce_shard_impl(const float* const* grads_peers_dev, const float* grads_mc, float* grads_local,
+                               long long shard_off, long long shard_n, int world, double* sumsq_local, void* stream_) {
   if (shard_n < 0 || (shard_n % 4) != 0 || (shard_off % 4) != 0 || world < 1) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (cudaMemsetAsync(sumsq_local, 0, sizeof(double), stream) != cudaSuccess) return MCA_ERR_CUDA;
   if (shard_n == 0) return MCA_OK;
-  dp_reduce_shard_kernel<<<num_sms() * 4, 256, 0, stream>>>(grads_peers_dev, grads_local, shard_off, shard_n, world,
+  dp_reduce_shard_kernel<<<num_sms() * 4, 256, 0, stream>>>(grads_peers_dev, grads_mc, grads_local, shard_off, shard_n, world,
                                                             sumsq_local);
   return check_launch();
 }
+
+static int dp_adamw_shard_impl(float* const* params_peers_dev, float* params_mc, int world, int rank, const float* grads_local,
+                              float* exp_avg, float* exp_avg_sq, long long shard_off, long long shard_n,
+                              const double* sumsq_slots, long long* step_dev, float* total_norm_out, float grad_scale,
+                              const mca_adamw_cfg* cfg_host, void* stream_);
 
 extern "C" int mca_dp_adamw_shard(float* const* params_peers_dev, int world, int rank, const float* grads_local,
                                   float* exp_avg, float* exp_avg_sq, long long shard_off, long long shard_n,
                                   const double* sumsq_slots, long long* step_dev, float* total_norm_out,
                                   float grad_scale, const mca_adamw_cfg* cfg_host, void* stream_) {
+  return dp_adamw_shard_impl(params_peers_dev, nullptr, world, rank, grads_local, exp_avg, exp_avg_sq, shard_off, shard_n,
+                             sumsq_slots, step_dev, total_norm_out, grad_scale, cfg_host, stream_);
+}
+
+extern "C" int mca_dp_adamw_shard_mc(float* const* params_peers_dev, float* params_multicast, int world, int rank,
+                                     const float* grads_local, float* exp_avg, float* exp_avg_sq, long long shard_off,
+                                     long long shard_n, const double* sumsq_slots, long long* step_dev,
+                                     float* total_norm_out, float grad_scale, const mca_adamw_cfg* cfg_host, void* stream_) {
+  if (params_multicast == nullptr) return MCA_ERR_ARG;
+  return dp_adamw_shard_impl(params_peers_dev, params_multicast, world, rank, grads_local, exp_avg, exp_avg_sq, shard_off,
+                             shard_n, sumsq_slots, step_dev, total_norm_out, grad_scale, cfg_host, stream_);
+}
+
+static int dp_adamw_shard_impl(float* const* params_peers_dev, float* params_mc, int world, int rank, const float* grads_local,
+                              float* exp_avg, float* exp_avg_sq, long long shard_off, long long shard_n,
+                              const double* sumsq_slots, long long* step_dev, float* total_norm_out, float grad_scale,
+                              const mca_adamw_cfg* cfg_host, void* stream_) {
   if (shard_n < 0 || (shard_n % 4) != 0 || (shard_off % 4) != 0 || world < 1 || rank < 0 || rank >= world)
     return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (shard_n > 0)
-    dp_adamw_shard_kernel<<<num_sms() * 4, 256, 0, stream>>>(params_peers_dev, world, rank, grads_local, exp_avg,
+    dp_adamw_shard_kernel<<<num_sms() * 4, 256, 0, stream>>>(params_peers_dev, params_mc, world, rank, grads_local, exp_avg,
                                                              exp_avg_sq, shard_off, shard_n, sumsq_slots, step_dev,
                                                              grad_scale, *cfg_host, total_norm_out);
   bump_step_only_kernel<<<1, 32, 0, stream>>>(step_dev);

@@ -39,9 +39,21 @@ __device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&v)[DH
   }
 }
 
-// grid = B*H*R, block 256.  qp [R, H*64] fp32 (already scaled), kv [B*N, 2*H*64] bf16 (K | V)
+__device__ __forceinline__ void load_row64(const float* p, float (&v)[DH]) {
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float4 q = p4[i];
+    v[4 * i + 0] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
+  }
+}
+__device__ __forceinline__ float kv_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float kv_to_float(float v) { return v; }
+
+// grid = B*H*R, block 256.  qp [R, H*64] fp32 (already scaled), kv [B*N, 2*H*64] (K | V), bf16 or (fp32-parity mode) fp32
+template <typename KV>
 __global__ void __launch_bounds__(256)
-pool_fwd_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ kv, const uint8_t* __restrict__ padding,
+pool_fwd_kernel(const float* __restrict__ qp, const KV* __restrict__ kv, const uint8_t* __restrict__ padding,
                 const uint8_t* __restrict__ keygrp, const uint32_t* __restrict__ rowbits, float* __restrict__ probs,
                 uint8_t* __restrict__ full_masked, float* __restrict__ out, int B, int H, int R, int N) {
   extern __shared__ float sc[];  // [N]
@@ -99,7 +111,7 @@ pool_fwd_kernel(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ 
   float acc = 0.f;
   for (int j = grp; j < N; j += 4) {
     const float p = sc[j];
-    if (p != 0.f) acc += p * __bfloat162float(kv[(static_cast<long long>(b) * N + j) * ld + H * DH + h * DH + c]);
+    if (p != 0.f) acc += p * kv_to_float(kv[(static_cast<long long>(b) * N + j) * ld + H * DH + h * DH + c]);
   }
   part[grp][c] = acc;
   __syncthreads();
@@ -669,11 +681,26 @@ extern "C" int mca_pool_attn_fwd(const float* qp, const void* kv, const uint8_t*
   }
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(pool_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  pool_fwd_kernel<<<B * H * R, 256, N * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+  pool_fwd_kernel<__nv_bfloat16><<<B * H * R, 256, N * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       qp, reinterpret_cast<const __nv_bfloat16*>(kv), padding, keygrp, rowbits, probs, full_masked, out, B, H, R, N);
+  return check_launch();
+}
+
+// fp32-parity mode (exact.cu): the same pooling on fp32 K | V rows [B*N, 2*H*64]
+extern "C" int mca_x_pool_attn_fwd_f32(const float* qp, const float* kv32, const uint8_t* padding, const uint8_t* keygrp,
+                                       const uint32_t* rowbits, float* probs, uint8_t* full_masked, float* out, int B,
+                                       int H, int R, int N, void* stream) {
+  if (B <= 0 || R <= 0 || N <= 0 || N * 4 > 200 * 1024) return MCA_ERR_SHAPE;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pool_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  pool_fwd_kernel<float><<<B * H * R, 256, N * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      qp, kv32, padding, keygrp, rowbits, probs, full_masked, out, B, H, R, N);
   return check_launch();
 }
 

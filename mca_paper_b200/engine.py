@@ -54,6 +54,12 @@ class Engine:
         self._ws_ready = False
         self._flat_ptrs = None
         self.check_finite = True
+        import os
+        self.parallel_encoders = os.environ.get("MCA_PARALLEL_ENCODERS", "1") != "0"
+        self.precision = "bf16"
+        self._xws = None
+        if os.environ.get("MCA_PRECISION", "bf16").lower() in ("fp32", "f32", "float32"):
+            self.precision = "fp32"
 
     # ------------------------------------------------------------------------------------------ parameters
     def _param_list(self):
@@ -75,12 +81,14 @@ class Engine:
             total += _round_up(p.numel(), ALIGN)
         self.device = dev
         flat, self._flat_peers = self._alloc_flat(total)
+        self._flat_mc = self._mc_last
         for name, p in params:
             o = offs[name]
             flat[o:o + p.numel()].copy_(p.detach().reshape(-1).to(torch.float32))
             p.data = flat[o:o + p.numel()].view(p.shape)
         self.flat, self.offs, self.n_flat = flat, offs, total
         self.flat_grad, self._grad_peers = self._alloc_flat(total)
+        self._grad_mc = self._mc_last
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
@@ -97,6 +105,7 @@ class Engine:
         (collective call: every rank allocates in the same order) and the peers' addresses are returned with it."""
         dev = self.device
         if not getattr(self, "_want_symm", False):
+            self._mc_last = 0
             return torch.zeros(total, device=dev, dtype=torch.float32), None
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -108,6 +117,9 @@ class Engine:
             raise _lib.MCAKernelError(f"symmetric-memory tensor outside its allocation (offset {off})")
         self._symm_keep = getattr(self, "_symm_keep", []) + [(buf, hdl)]
         peers = torch.tensor([int(p) + off for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        # NVSwitch multicast mapping of the same allocation (NVLS), 0 when the fabric / driver has none
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        self._mc_last = mc + off if mc else 0
         return buf, peers
 
     def pview(self, name):  # fp32 view of a parameter inside the flat buffer
@@ -210,6 +222,94 @@ class Engine:
 
     def pack_weights(self):
         call("mca_pack_weights", P(self.flat), P(self.arena), P(self.pack_descs), self.n_desc, S())
+        if self.precision == "fp32":
+            call("mca_x_pack_weights_split", P(self.flat), P(self._exact_ws()["arena3"]), P(self.pack_descs), self.n_desc, S())
+
+    # ------------------------------------------------------------------------------------------ fp32-parity mode
+    def set_precision(self, mode: str):
+        """"bf16" (default): bf16 tensor-core operands, fp32 accumulation — within 2e-2 of the fp32 reference.
+        "fp32": the fp32-parity FORWARD (csrc/exact.cu): every contraction as a 3-term bf16 split product on the same
+        tcgen05 GEMM (16 significand bits per operand), fp32 attention core, GEGLU and pooling — loss and embeddings
+        within 1e-3 of the reference (train_accel_gpu.py:21: fp32, no autocast).  The backward stays on the bf16 kernels
+        and consumes the bf16 copies this forward saves (north_star sets no 1e-3 bar for gradients).  Also selectable
+        with MCA_PRECISION=fp32."""
+        if mode not in ("bf16", "fp32"):
+            raise ValueError(f"precision {mode!r}: expected 'bf16' or 'fp32'")
+        if mode == "fp32" and self.eao:
+            raise NotImplementedError("fp32-parity mode covers the MCA / MMA models (the EAO baseline pools bf16 tokens)")
+        self.precision = mode
+        if self._ws_ready:
+            self.pack_weights()
+
+    def _exact_ws(self):
+        if self._xws is None:
+            dev, M, IP = self.device, self.M, self.IP
+            f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+            x = {"arena3": torch.zeros(3 * self.arena.numel(), device=dev, dtype=torch.bfloat16),
+                 "x1_32": f32(M, D), "qkv32": f32(M, 3 * D), "ao32": f32(M, D), "x3_32": f32(M, D), "u32": f32(M, 2 * IP),
+                 "xf32": f32(M, D), "kv32": f32(M, 2 * D),
+                 "a3": torch.empty(M * 3 * max(IP, D), device=dev, dtype=torch.bfloat16), "enc": {}}
+            for name, enc in zip(self.plan.names, self.model.encoder_specs):
+                rows = self.B * enc["max_tokens"]
+                if enc["type"] in ("EmbeddedSequenceEncoder", "PatchEncoder"):
+                    x["enc"][name] = torch.empty(rows, 3 * self.enc_kpad[name], device=dev, dtype=torch.bfloat16)
+                elif enc["type"] in ("TabularEncoder", "SparseTabularEncoder"):
+                    x["enc"][name] = torch.empty(rows, 3 * D, device=dev, dtype=torch.bfloat16)
+            self._xws = x
+        return self._xws
+
+    def W3(self, key):  # [W_hi | W_lo | W_hi] kernel-layout weight of the split product
+        o, r, c = self.w[key]
+        return self._exact_ws()["arena3"][3 * o:3 * o + 3 * r * c].view(r, 3 * c)
+
+    def _split(self, src32, rows, cols):
+        """fp32 [rows, cols] -> the [hi | hi | lo] operand [rows, 3*cols] in the shared scratch."""
+        a3 = self._exact_ws()["a3"][:rows * 3 * cols].view(rows, 3 * cols)
+        call("mca_x_split_f32", P(src32), src32.stride(0), P(a3), rows, cols, cols, 0, S())
+        return a3
+
+    def _proj(self, name, enc_key, a3, kp, bias, out):
+        """Encoder projection of the split operand a3 [rows, 3*kp] (or the bf16 one) into z."""
+        rows = a3.shape[0]
+        ops.gemm(a3, 0, self.W3(enc_key), 0, rows, D, 3 * kp, _lib.EPI_F32, out, bias=bias)
+
+    def trunk_forward_exact(self, batch):
+        """trunk_forward in fp32-parity mode (set_precision): same buffers for the backward, fp32 values in between."""
+        ws, X, M, IP = self.ws, self._exact_ws(), self.M, self.IP
+        ws["nonfinite"].zero_()
+        ws["drop_ctr"].add_(1)
+        self.build_offsets(batch)
+        self.encode(batch)
+        for l in range(self.depth):
+            p = f"layers.{l}."
+            gamma, beta = self.pview(p + "norm.gamma"), self.model.layers[l].norm.beta
+            # x1 = LN(x)                                                     (model.py:118, shared LayerNorm: Q1)
+            ops.layernorm512_fwd(ws["xa"][l], gamma, beta, X["x1_32"], ws["x1_16"][l], ws["st1"][l], M)
+            ops.gemm(self._split(X["x1_32"], M, D), 0, self.W3(p + "qkv"), 0, M, 3 * D, 3 * D, _lib.EPI_F32, X["qkv32"])
+            call("mca_cast_f32_bf16", P(X["qkv32"]), 3 * D, P(ws["qkv"][l]), 3 * D, M, 3 * D, S())
+            call("mca_x_attn_fwd_f32", P(X["qkv32"]), P(self.rowbits), P(self.keygrp), P(ws["padding"]), P(ws["vmean"]),
+                 P(X["ao32"]), P(ws["ao"][l]), P(ws["lse"][l]), self.B, self.N, self.H, S())
+            # x2 = attn(x1) Wo^T + x1                                        (model.py:119)
+            ops.gemm(self._split(X["ao32"], M, D), 0, self.W3(p + "out"), 0, M, D, 3 * D, _lib.EPI_RESID, ws["x2"][l],
+                     aux0=X["x1_32"], ldaux=D)
+            # x3 = LN(x2);  x' = geglu(x3 W1^T) W2^T + x3                    (model.py:120-122, 35-54)
+            ops.layernorm512_fwd(ws["x2"][l], gamma, beta, X["x3_32"], ws["x3_16"][l], ws["st2"][l], M)
+            ops.gemm(self._split(X["x3_32"], M, D), 0, self.W3(p + "ff1"), 0, M, 2 * IP, 3 * D, _lib.EPI_F32, X["u32"])
+            h3 = X["a3"][:M * 3 * IP].view(M, 3 * IP)
+            call("mca_x_geglu_f32", P(X["u32"]), P(h3), P(ws["h"][l]), P(ws["u"][l]), M, IP, S())
+            ops.gemm(h3, 0, self.W3(p + "ff2"), 0, M, D, 3 * IP, _lib.EPI_RESID, ws["xa"][l + 1], aux0=X["x3_32"], ldaux=D)
+        ops.layernorm512_fwd(ws["xa"][self.depth], self.pview("norm.gamma"), self.model.norm.beta, X["xf32"], ws["xf_16"],
+                             ws["stF"], M)
+        # attention pooling on the final-normed tokens (model.py:470-473)
+        ops.gemm(self._split(X["xf32"], M, D), 0, self.W3("attn_pool.kv"), 0, M, 2 * D, 3 * D, _lib.EPI_F32, X["kv32"])
+        call("mca_cast_f32_bf16", P(X["kv32"]), 2 * D, P(ws["kvp"]), 2 * D, M, 2 * D, S())
+        rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
+        ops.small_gemm(rt, D, 1, wq, D, 1, ws["qp"], D, self.R, D, D, alpha=DH ** -0.5)
+        call("mca_x_pool_attn_fwd_f32", P(ws["qp"]), P(X["kv32"]), P(ws["padding"]), P(self.keygrp), P(self.pool_rowbits),
+             P(ws["probs"]), P(ws["fm"]), P(ws["po"]), self.B, self.H, self.R, self.N, S())
+        ops.small_gemm(ws["po"].view(self.B * self.R, D), D, 1, wo, D, 1, ws["pooled"].view(self.B * self.R, D), D,
+                       self.B * self.R, D, D, add=rt, ldadd=D, add_rows=self.R)
+        return ws["pooled"]
 
     # ------------------------------------------------------------------------------------------ workspaces
     def _alloc_workspace(self, dev):
@@ -346,10 +446,18 @@ class Engine:
             "slots_peers": i64([b + 4 * (n_p + n_d + 64) for b in base]),
             "sumsq_local": torch.zeros(1, dtype=torch.float64, device=dev),
             "grad_peers": self._grad_peers, "param_peers": self._flat_peers,
+            # in-switch reduction / replication of the optimiser exchange (multimem.ld_reduce / multimem.st) when every
+            # rank got a multicast mapping of both flat buffers
+            "grad_mc": self._grad_mc, "param_mc": self._flat_mc, "multimem": False,
             "epoch": torch.zeros(1, dtype=torch.int32, device=dev),
             # pinned host memory (device-addressable under UVA): still readable after the barrier kernel trapped
             "err": torch.zeros(1, dtype=torch.int32).pin_memory(),
         }
+        import os
+        want_mc = os.environ.get("MCA_MULTIMEM", "1") != "0" and self._grad_mc != 0 and self._flat_mc != 0
+        ok = torch.tensor([1 if want_mc else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)   # collective choice, like the P2P-or-NCCL one
+        self._p2p["multimem"] = bool(int(ok.item()))
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)  # every rank's flags are zero before anybody raises one
 
@@ -434,11 +542,61 @@ class Engine:
         o = pl.offsets[i] * self.B
         return self.ws["pad_mod"][o:o + self.B * pl.lengths[i]]
 
+    # The modality encoders are independent chains of small kernels (a [400..12000]-row LayerNorm / GEMM / LayerNorm does
+    # not fill 148 SMs and costs ~10 us of launch + pipeline latency per kernel whatever its size): forward and backward
+    # run them on parallel streams — graph branches once the step is captured — forked from and joined to the step's stream.
+    def _branches(self, n):
+        """[(stream, is_main)] for n independent chains: the largest first on the current stream, the others on side streams
+        that wait for everything enqueued so far."""
+        main = torch.cuda.current_stream()
+        if n <= 1 or not self.parallel_encoders:
+            return [main] * n, main
+        if getattr(self, "_side_streams", None) is None or len(self._side_streams) < n - 1:
+            self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(n - 1)]
+            self._fork_ev = torch.cuda.Event()
+            self._join_ev = [torch.cuda.Event() for _ in range(n - 1)]
+        self._fork_ev.record(main)
+        streams = [main] + self._side_streams[:n - 1]
+        for st in streams[1:]:
+            st.wait_event(self._fork_ev)
+        return streams, main
+
+    def _join(self, streams, main):
+        k = 0
+        for st in streams:
+            if st is not main:
+                self._join_ev[k].record(st)
+                main.wait_event(self._join_ev[k])
+                k += 1
+
+    def _encoder_order(self):
+        """Encoder indices, largest token count first (it takes the main stream)."""
+        specs = self.model.encoder_specs
+        return sorted(range(len(specs)), key=lambda i: -int(specs[i]["max_tokens"]) * int(specs[i].get("input_size", 512)))
+
     def encode(self, batch):
         """Encoders write straight into the packed token buffer xa[0] (no `pack` copy, model.py:464)."""
+        pl = self.plan
+        order = self._encoder_order()
+        streams, main = self._branches(len(order))
+        for st, i in zip(streams, order):
+            with torch.cuda.stream(st):
+                self._encode_one(i, batch)
+        self._join(streams, main)
+        x0 = self.ws["xa"][0]
+        if pl.F:
+            call("mca_broadcast_rows", P(self.pview("fusion_tokens")), P(x0), pl.F, D, self.B, self.N, pl.n_tok, S())
+        if self.eao:
+            # every modality is encoded once (model.py:576-578); the passes it takes part in read replicas (model.py:584)
+            xv = x0.view(self.B, self.N, D)
+            for dst, src, L in pl.replicas:
+                xv[:, dst:dst + L].copy_(xv[:, src:src + L])
+
+    def _encode_one(self, i, batch):
         pl, ws = self.plan, self.ws
         x0 = ws["xa"][0]
-        for i, (name, enc) in enumerate(zip(pl.names, self.model.encoder_specs)):
+        name, enc = pl.names[i], self.model.encoder_specs[i]
+        if True:
             pre = f"encoders.{name}."
             L = enc["max_tokens"]
             rows = self.B * L
@@ -453,8 +611,14 @@ class Engine:
                 call("mca_layernorm_in_fwd", P(tok), P(self.pview(pre + "token_encoder.0.weight")),
                      P(self.pview(pre + "token_encoder.0.bias")), P(pad), P(e["y"]), P(e["st_in"]), kin, kp, rows,
                      P(ws["nonfinite"]), S())
-                ops.gemm(e["y"], 0, self.W(pre + "proj"), 0, rows, D, kp, _lib.EPI_F32, e["z"],
-                         bias=self.pview(pre + "token_encoder.1.bias"))
+                if self.precision == "fp32":
+                    y3 = self._exact_ws()["enc"][name]
+                    call("mca_x_layernorm_in_split", P(tok), P(self.pview(pre + "token_encoder.0.weight")),
+                         P(self.pview(pre + "token_encoder.0.bias")), P(pad), P(y3), kin, kp, rows, S())
+                    self._proj(name, pre + "proj", y3, kp, self.pview(pre + "token_encoder.1.bias"), e["z"])
+                else:
+                    ops.gemm(e["y"], 0, self.W(pre + "proj"), 0, rows, D, kp, _lib.EPI_F32, e["z"],
+                             bias=self.pview(pre + "token_encoder.1.bias"))
                 ops.layernorm512_fwd(e["z"], self.pview(pre + "token_encoder.2.weight"),
                                      self.pview(pre + "token_encoder.2.bias"), x0, None, e["st_out"], rows, pad=pad,
                                      pe=self.model.encoders[name].positional_encoder.pe, seg_len=L,
@@ -469,8 +633,7 @@ class Engine:
                 call("mca_tabular_fwd", P(vals), P(self.pview(pre + "value_encoder.linear1.weight")),
                      P(self.pview(pre + "value_encoder.linear1.bias")), P(e["h1"]), P(e["vpad"]),
                      float(enc.get("max_value", 10000)), float(enc.get("padding_idx", -1)), D, rows, S())
-                ops.gemm(e["h1"], 0, self.W(pre + "proj"), 0, rows, D, D, _lib.EPI_F32, e["z"],
-                         bias=self.pview(pre + "value_encoder.linear2.bias"))
+                self._tabular_proj(name, pre, enc, e, vals, rows)
                 ops.layernorm512_fwd(e["z"], self.pview(pre + "value_encoder.norm.weight"),
                                      self.pview(pre + "value_encoder.norm.bias"), x0, None, e["st_out"], rows,
                                      pad=e["vpad"], pe=emb, seg_len=L, out_rows_per_b=self.N, out_row_off=pl.offsets[i])
@@ -495,8 +658,7 @@ class Engine:
                 call("mca_tabular_fwd", P(vals), P(self.pview(pre + "value_encoder.linear1.weight")),
                      P(self.pview(pre + "value_encoder.linear1.bias")), P(e["h1"]), P(e["vpad"]),
                      float(enc.get("max_value", 10000)), float(enc.get("padding_idx", 0)), D, rows, S())
-                ops.gemm(e["h1"], 0, self.W(pre + "proj"), 0, rows, D, D, _lib.EPI_F32, e["z"],
-                         bias=self.pview(pre + "value_encoder.linear2.bias"))
+                self._tabular_proj(name, pre, enc, e, vals, rows)
                 ops.layernorm512_fwd(e["z"], self.pview(pre + "value_encoder.norm.weight"),
                                      self.pview(pre + "value_encoder.norm.bias"), x0, None, e["st_out"], rows,
                                      pad=e["vpad"], seg_len=L, out_rows_per_b=self.N, out_row_off=pl.offsets[i])
@@ -508,8 +670,14 @@ class Engine:
                 call("mca_layernorm_in_fwd", P(e["ptok"]), P(self.pview(pre + "batch_to_tokens.1.weight")),
                      P(self.pview(pre + "batch_to_tokens.1.bias")), None, P(e["y"]), P(e["st_in"]), kin, kp, rows,
                      P(ws["nonfinite"]), S())
-                ops.gemm(e["y"], 0, self.W(pre + "proj"), 0, rows, D, kp, _lib.EPI_F32, e["z"],
-                         bias=self.pview(pre + "batch_to_tokens.2.bias"))
+                if self.precision == "fp32":
+                    y3 = self._exact_ws()["enc"][name]
+                    call("mca_x_layernorm_in_split", P(e["ptok"]), P(self.pview(pre + "batch_to_tokens.1.weight")),
+                         P(self.pview(pre + "batch_to_tokens.1.bias")), None, P(y3), kin, kp, rows, S())
+                    self._proj(name, pre + "proj", y3, kp, self.pview(pre + "batch_to_tokens.2.bias"), e["z"])
+                else:
+                    ops.gemm(e["y"], 0, self.W(pre + "proj"), 0, rows, D, kp, _lib.EPI_F32, e["z"],
+                             bias=self.pview(pre + "batch_to_tokens.2.bias"))
                 ops.layernorm512_fwd(e["z"], self.pview(pre + "batch_to_tokens.3.weight"),
                                      self.pview(pre + "batch_to_tokens.3.bias"), x0, None, e["st_out"], rows,
                                      pe=self.pview(pre + "embedding.weight"), seg_len=L, out_rows_per_b=self.N,
@@ -517,13 +685,17 @@ class Engine:
                 self._dropout(i, enc, x0)
             else:
                 raise NotImplementedError(f"unknown encoder type {enc['type']}")
-        if pl.F:
-            call("mca_broadcast_rows", P(self.pview("fusion_tokens")), P(x0), pl.F, D, self.B, self.N, pl.n_tok, S())
-        if self.eao:
-            # every modality is encoded once (model.py:576-578); the passes it takes part in read replicas (model.py:584)
-            xv = x0.view(self.B, self.N, D)
-            for dst, src, L in pl.replicas:
-                xv[:, dst:dst + L].copy_(xv[:, src:src + L])
+
+    def _tabular_proj(self, name, pre, enc, e, vals, rows):
+        """linear2 of ContinuousValueEncoder (encoders.py:60-75) on h1; fp32-parity mode recomputes h1 as a split operand."""
+        if self.precision == "fp32":
+            h3 = self._exact_ws()["enc"][name]
+            call("mca_x_tabular_split", P(vals), P(self.pview(pre + "value_encoder.linear1.weight")),
+                 P(self.pview(pre + "value_encoder.linear1.bias")), P(h3), float(enc.get("max_value", 10000)), D, rows, S())
+            self._proj(name, pre + "proj", h3, D, self.pview(pre + "value_encoder.linear2.bias"), e["z"])
+        else:
+            ops.gemm(e["h1"], 0, self.W(pre + "proj"), 0, rows, D, D, _lib.EPI_F32, e["z"],
+                     bias=self.pview(pre + "value_encoder.linear2.bias"))
 
     def _dropout(self, i, enc, rows32):
         """nn.Dropout of PatchEncoder (encoders.py:274) on the modality's rows of `rows32` (tokens in the forward, their
@@ -541,6 +713,8 @@ class Engine:
 
     def trunk_forward(self, batch):
         """encoders -> depth x [LN, QKV, attention, out-proj(+res), LN, FF1(GEGLU), FF2(+res)] -> LN -> pooling."""
+        if self.precision == "fp32":
+            return self.trunk_forward_exact(batch)
         ws, M, IP = self.ws, self.M, self.IP
         ws["nonfinite"].zero_()
         ws["drop_ctr"].add_(1)
@@ -719,10 +893,20 @@ class Engine:
              self.B, self.N, self.H, S())
 
     def encode_backward(self, dx0):
-        pl, ws = self.plan, self.ws
+        pl = self.plan
+        order = self._encoder_order()
+        streams, main = self._branches(len(order))
         if pl.F:
             call("mca_batchsum_rows", P(dx0), P(self.gview("fusion_tokens")), pl.F, D, self.B, self.N, pl.n_tok, 1, S())
-        for i, (name, enc) in enumerate(zip(pl.names, self.model.encoder_specs)):
+        for st, i in zip(streams, order):
+            with torch.cuda.stream(st):
+                self._encode_backward_one(i, dx0)
+        self._join(streams, main)
+
+    def _encode_backward_one(self, i, dx0):
+        pl, ws = self.plan, self.ws
+        name, enc = pl.names[i], self.model.encoder_specs[i]
+        if True:
             pre = f"encoders.{name}."
             L = enc["max_tokens"]
             rows = self.B * L
@@ -874,11 +1058,19 @@ class Engine:
             p = self._p2p
             off, n = self.shard()
             self.xgpu_barrier()                                  # every rank's gradient buffer is complete
-            call("mca_dp_reduce_shard", P(p["grad_peers"]), P(self.flat_grad), off, n, self.world, P(p["sumsq_local"]), S())
+            if p["multimem"]:
+                call("mca_dp_reduce_shard_mc", p["grad_mc"], P(self.flat_grad), off, n, self.world, P(p["sumsq_local"]), S())
+            else:
+                call("mca_dp_reduce_shard", P(p["grad_peers"]), P(self.flat_grad), off, n, self.world, P(p["sumsq_local"]), S())
             self.xgpu_barrier(payload=p["sumsq_local"])          # + the G partial sums of squares, everywhere
-            call("mca_dp_adamw_shard", P(p["param_peers"]), self.world, self.rank, P(self.flat_grad), P(self.exp_avg),
-                 P(self.exp_avg_sq), off, n, P(p["slots"]), P(self.step_dev), P(self.total_norm), 1.0 / self.world,
-                 ctypes.addressof(self.adamw_cfg), S())
+            if p["multimem"]:
+                call("mca_dp_adamw_shard_mc", P(p["param_peers"]), p["param_mc"], self.world, self.rank, P(self.flat_grad),
+                     P(self.exp_avg), P(self.exp_avg_sq), off, n, P(p["slots"]), P(self.step_dev), P(self.total_norm),
+                     1.0 / self.world, ctypes.addressof(self.adamw_cfg), S())
+            else:
+                call("mca_dp_adamw_shard", P(p["param_peers"]), self.world, self.rank, P(self.flat_grad), P(self.exp_avg),
+                     P(self.exp_avg_sq), off, n, P(p["slots"]), P(self.step_dev), P(self.total_norm), 1.0 / self.world,
+                     ctypes.addressof(self.adamw_cfg), S())
             self.xgpu_barrier()                                  # every parameter shard has landed
             self.pack_weights()
             return

@@ -53,6 +53,8 @@ _SIGS = {
     "mca_dp_reduce_shard": [VP, VP, I64, I64, I32, VP, VP],
     "mca_dp_adamw_shard": [VP, I32, I32, VP, VP, VP, I64, I64, VP, VP, VP, F32, VP, VP],
     "mca_p2p_reduce_rows": [VP, I64, VP, I64, I32, VP],
+    "mca_dp_reduce_shard_mc": [VP, VP, I64, I64, I32, VP, VP],
+    "mca_dp_adamw_shard_mc": [VP, VP, I32, I32, VP, VP, VP, I64, I64, VP, VP, VP, F32, VP, VP],
     "mca_clip_adamw_step": [VP, VP, VP, VP, I64, VP, VP, VP, F32, VP, VP],
     "mca_embedding_renorm_indexed": [VP, VP, I64, I32, I32, F32, VP, VP, VP],
     "mca_embedding_gather": [VP, VP, I32, I32, I32, I32, VP, VP, I32, I32, I32, VP],
@@ -76,6 +78,13 @@ _SIGS = {
     "mca_cross_entropy_fwd": [VP, I64, VP, I32, I32, F32, VP, VP, VP],
     "mca_cross_entropy_bwd": [VP, I64, VP, I32, I32, F32, VP, VP, VP, VP, VP, VP],
     "mca_attn_probs": [VP, VP, VP, VP, VP, I32, I32, I32, VP, VP],
+    "mca_x_split_f32": [VP, I64, VP, I64, I32, I32, I32, VP],
+    "mca_x_pack_weights_split": [VP, VP, VP, I32, VP],
+    "mca_x_layernorm_in_split": [VP, VP, VP, VP, VP, I32, I32, I64, VP],
+    "mca_x_tabular_split": [VP, VP, VP, VP, F32, I32, I64, VP],
+    "mca_x_geglu_f32": [VP, VP, VP, VP, I64, I32, VP],
+    "mca_x_attn_fwd_f32": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
+    "mca_x_pool_attn_fwd_f32": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS.keys())
@@ -108,7 +117,7 @@ def S():
 
 # kernels launched by each entry point (memsets not counted) — bench.py reports the per-step total
 KERNELS_PER_CALL = {"mca_build_offsets": 2, "mca_attn_fwd": 2, "mca_attn_bwd": 3, "mca_pool_attn_bwd": 2,
-                    "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3, "mca_dp_adamw_shard": 2,
+                    "mca_contrastive_allpairs_fwd": 3, "mca_clip_adamw_step": 3, "mca_dp_adamw_shard": 2, "mca_dp_adamw_shard_mc": 2,
                     "mca_embedding_renorm_indexed": 2, "mca_mean_pool_fwd": 2, "mca_alignment": 2, "mca_uniformity": 3, "mca_retrieval_ranks": 4}
 COUNT = {"n": 0}
 PROFILE = {"on": False, "events": []}

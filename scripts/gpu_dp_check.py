@@ -101,7 +101,7 @@ torch.cuda.empty_cache()
 model = model.to(dev)
 tr = Trainer(model, lr=LR, clip=CLIP, schedule="constant", use_graphs=True)
 eng = tr.eng
-exch = "p2p (symmetric memory)" if eng._p2p is not None else "nccl"
+exch = ("p2p (symmetric memory" + (", NVSwitch multimem optimiser exchange)" if eng._p2p["multimem"] else ")")) if eng._p2p is not None else "nccl"
 tr.stage(batches[rank])
 tr._seg_forward()
 tr._seg_loss()
@@ -130,12 +130,20 @@ if eng._p2p is not None:
     p2 = eng._p2p
     off, n = eng.shard()
     eng.xgpu_barrier()
-    call("mca_dp_reduce_shard", P(p2["grad_peers"]), P(eng.flat_grad), off, n, world, P(p2["sumsq_local"]), STREAM())
+    if p2["multimem"]:   # NVSwitch in-fabric reduction (multimem.ld_reduce) / replication (multimem.st)
+        call("mca_dp_reduce_shard_mc", p2["grad_mc"], P(eng.flat_grad), off, n, world, P(p2["sumsq_local"]), STREAM())
+    else:
+        call("mca_dp_reduce_shard", P(p2["grad_peers"]), P(eng.flat_grad), off, n, world, P(p2["sumsq_local"]), STREAM())
     torch.cuda.synchronize()
     mine = (eng.flat_grad[off:off + n] / world).clone()          # the reduced mean gradient of this rank's shard
     eng.xgpu_barrier(payload=p2["sumsq_local"])
-    call("mca_dp_adamw_shard", P(p2["param_peers"]), world, rank, P(eng.flat_grad), P(eng.exp_avg), P(eng.exp_avg_sq), off, n,
-         P(p2["slots"]), P(eng.step_dev), P(eng.total_norm), 1.0 / world, ctypes.addressof(eng.adamw_cfg), STREAM())
+    if p2["multimem"]:
+        call("mca_dp_adamw_shard_mc", P(p2["param_peers"]), p2["param_mc"], world, rank, P(eng.flat_grad), P(eng.exp_avg),
+             P(eng.exp_avg_sq), off, n, P(p2["slots"]), P(eng.step_dev), P(eng.total_norm), 1.0 / world,
+             ctypes.addressof(eng.adamw_cfg), STREAM())
+    else:
+        call("mca_dp_adamw_shard", P(p2["param_peers"]), world, rank, P(eng.flat_grad), P(eng.exp_avg), P(eng.exp_avg_sq), off, n,
+             P(p2["slots"]), P(eng.step_dev), P(eng.total_norm), 1.0 / world, ctypes.addressof(eng.adamw_cfg), STREAM())
     eng.xgpu_barrier()
     eng.pack_weights()
     per = eng.shard_size(eng.n_flat, world)
@@ -175,10 +183,10 @@ chk_g = [red[eng.offs[nm]:eng.offs[nm] + p.numel()].clone() for nm, p in eng._pa
 O.clip_adamw_step(chk_p, chk_g, [torch.zeros_like(x) for x in chk_p], [torch.zeros_like(x) for x in chk_p], 1, lr=LR, max_norm=CLIP)
 worst_p = max(rel(eng.flat[eng.offs[nm]:eng.offs[nm] + p.numel()], q) for (nm, p), q in zip(eng._param_list(), chk_p))
 assert worst_p < 1e-6, worst_p
-# ... and close to the oracle's own step-1 parameters (different gradient rounding: loose)
-worst_po = max(rel(eng.flat[eng.offs[nm]:eng.offs[nm] + p.numel()], q) for (nm, p), q in zip(eng._param_list(), o_params))
-say(f"parameters after step 1: vs oracle AdamW on the same gradient {worst_p:.2e} (bar 1e-6); vs the oracle's own step {worst_po:.2e}")
-assert worst_po < 1e-3, worst_po
+say(f"parameters after step 1: vs oracle AdamW on the same reduced gradient {worst_p:.2e} (bar 1e-6)")
+# (the oracle's own post-step parameters are not a usable target: at step 1 AdamW moves every element by lr * sign(g), so two
+# differently rounded gradients disagree by O(1) relative on zero-initialised tensors; the loss of step 2 below is the check
+# that the two trajectories stay together)
 
 
 def replicas_identical():
