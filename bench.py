@@ -320,6 +320,8 @@ def main():
     ap.add_argument("--variant", default="full")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--varlen", default=None, choices=["exact", "fast", "off"],
+                    help="varlen query skipping of the attention kernels (default: the engine's, MCA_VARLEN or 'exact')")
     ap.add_argument("--profile-step", action="store_true",
                     help="for ncu --profile-from-start off: warm up, then bracket exactly ONE eager training step with "
                          "cudaProfilerStart/Stop and exit (no timing, no JSON line: a number taken under a profiler is not a bench value)")
@@ -338,6 +340,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL's "NCCL version ..." banner goes to stdout under NCCL_DEBUG=VERSION/INFO: keep stdout to the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=dev)
 
     from mca_paper_b200 import config as C, ops, synthetic as S
@@ -351,8 +355,12 @@ def main():
     trainer = Trainer(model, lr=float(cfg["lr"]), clip=float(cfg["clip"]), schedule="cosine",
                       warmup_steps=int(cfg["num_warmup_steps"]), total_steps=100000, use_graphs=not args.no_graphs)
     eng = trainer.eng
+    if args.varlen is not None:
+        eng.set_varlen(args.varlen)
     host_batch = S.make_batch(cfg, seed=1 + rank, variant=args.variant)
     B = eng.B
+    live_tokens = 1.0 - float(sum(float(d["attention_mask"].to(torch.bool).sum()) for d in host_batch.values()
+                                  if "attention_mask" in d)) / float(B * eng.N)
 
     def barrier():
         if world > 1:
@@ -588,6 +596,7 @@ def main():
                        "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graphs": not args.no_graphs,
                        "dp_exchange": ("none" if world == 1 else ("peer memory (push/pull kernels + flag barriers, one graph)"
                                                                  if eng._p2p is not None else "nccl")),
+                       "varlen": eng.varlen, "live_token_fraction": live_tokens,
                        "l2": "per-step working set (~2 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "precision": "bf16 tensor-core operands, fp32 accumulate, fp32 master weights/residual stream/LN/softmax/loss"},
             "clocks": clocks,

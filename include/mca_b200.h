@@ -184,17 +184,29 @@ int mca_cast_f32_bf16(const float* src, long long ld_src, void* dst, long long l
 /* Block-sparse masked multi-head attention (model.py:85-100), dim_head = 64.  qkv: bf16 [B*N, 3*H*64] = (Q*scale | K | V),
  * out: bf16 [B*N, H*64], lse: [B,H,N] natural-log row log-sum-exp (+inf marks a fully masked row).
  * q_tiles may be listed in any order (heaviest first balances the SMs); tile_grp[n_kt] = key group shared by all
- * keys of the tile or 255 when the tile mixes groups; kt_live = live-key bit words from mca_build_offsets. */
+ * keys of the tile or 255 when the tile mixes groups; kt_live = live-key bit words from mca_build_offsets.
+ * Varlen query skipping (north_star subsystem 1: tokens of absent / padded modalities are never read): skip_ok [B] bytes
+ * from mca_query_skip_flags (NULL = off); for a sample whose flag is set, a query tile whose rows are ALL padded
+ * (padding [B,N]) visits no key tile: its rows get the fully-masked value and LSE = +inf, the backward leaves it out. */
 int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int n_qt, const mca_attn_ref* kt_list,
                  const mca_attn_tile* k_tiles, int n_kt, const uint32_t* rowbits, const uint8_t* keygrp,
-                 const uint8_t* tile_grp, const uint8_t* kt_class, const uint32_t* kt_live, const int* any_absent,
-                 float* vmean, void* out, float* lse, int B, int N, int H, void* stream);
+                 const uint8_t* tile_grp, const uint8_t* kt_class, const uint32_t* kt_live, const uint8_t* padding,
+                 const uint8_t* skip_ok, const int* any_absent, float* vmean, void* out, float* lse, int B, int N, int H,
+                 void* stream);
 /* Backward: dout bf16 [B*N, H*64] -> dqkv bf16 [B*N, 3*H*64].  k_tiles_q lists, for every key tile, the query tiles
  * that attend it (transposed schedule).  dq_accum: fp32 [B*N, H*64] scratch, delta: [B,H,N], ucorr: [B, H*64]. */
 int mca_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const mca_attn_qtile* k_tiles_q,
                  int n_kt, const mca_attn_ref* qt_list, const mca_attn_tile* q_tiles, int n_qt, const uint32_t* rowbits,
                  const uint8_t* keygrp, const uint8_t* tile_grp, const uint8_t* padding, const uint8_t* kt_class,
-                 float* delta, float* ucorr, float* dq_accum, void* dqkv, int B, int N, int H, void* stream);
+                 const uint8_t* skip_ok, float* delta, float* ucorr, float* dq_accum, void* dqkv, int B, int N, int H,
+                 void* stream);
+/* skip_ok[b] for the varlen query skipping above, from `present` [B, n_blk] of mca_build_offsets (first n_mod columns =
+ * modalities).  mode 0: never; 1 (exact): only samples in which EVERY modality is present — padded rows of such a sample
+ * feed nothing (every consumer masks padded keys), so results are unchanged; with an absent modality the reference's
+ * fully-masked pooling row averages ALL N final tokens, padded ones included (quirk Q4/Q8), and they must be computed;
+ * 2 (fast): every sample — padded query rows are never scored; the pooled embedding of an ABSENT modality (a negative
+ * column of the loss) then averages substitute values for the padded rows: a documented approximation. */
+int mca_query_skip_flags(const uint8_t* present, int n_blk, int n_mod, int B, int mode, uint8_t* skip_ok, void* stream);
 
 /* Attention pooling core (model.py:472-473): qp [R,H*64] fp32 scaled queries, kv bf16 [B*N, 2*H*64] (K|V),
  * rowbits[R] allowed key groups per pooled row, probs [B,H,R,N] saved for the backward, out [B,R,H*64]. */
@@ -322,6 +334,20 @@ int mca_uniformity(const float* x, long long M, int D, float t, int norm, float*
  * IndexError; the host wrapper checks). */
 int mca_retrieval_ranks(const float* emb, const float* targets, const long long* idx, long long M, long long T, int D,
                         float* inv_e, float* inv_t, float* own, long long* ranks, void* stream);
+
+/* ---- Linear probe on frozen embeddings (lp_accel_gpu.py:22-35 FineTuneDataset, :100-104 nn.Linear(num_emb, num_labels),
+ * :118-131 losses, :160-231 epoch loop with clip_grad_norm_ / AdamW / get_scheduler stepped once per batch).  One launch =
+ * one EPOCH: a thread-block cluster keeps the parameters and AdamW moments in shared memory and exchanges the per-CTA
+ * gradient partials through distributed shared memory.  X [rows, 512], Y [rows, n_out] fp32; order [n] = dataset indices in
+ * visiting order (the RandomSampler permutation; arange for evaluation); state = [3][n_out*512 + n_out] (W row-major then
+ * bias; exp_avg; exp_avg_sq); loss_kind 0 L1Loss, 1 MSELoss, 2 BCEWithLogitsLoss, 3 CrossEntropyLoss with probability
+ * targets (all mean-reduced); train = 0 evaluates (no update).  pred [rows, n_out] gets every visited row's prediction,
+ * *loss_sum += sum over the batches of the batch-mean loss (the reference's epoch_loss).  n_out <= 8. */
+int mca_probe_epoch(const float* X, const float* Y, const int* order, int n, int batch_size, int n_out, int loss_kind,
+                    int train, float* state, long long* step_dev, const mca_adamw_cfg* cfg_host, float* pred,
+                    double* loss_sum, float* last_grad_norm, void* stream);
+/* torchmetrics.PearsonCorrCoef of (pred, y) over n values (lp_accel_gpu.py:148-149). */
+int mca_probe_pcc(const float* pred, const float* y, long long n, float* out, void* stream);
 
 /* ---- fp32-parity forward mode (csrc/exact.cu).  The reference computes in fp32 end to end (train_accel_gpu.py:21 default
  * Accelerator(), no autocast; model.py:73-105), and north_star asks for loss / embeddings within 1e-3 of it.  Every dense

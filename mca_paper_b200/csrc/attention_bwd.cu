@@ -67,6 +67,7 @@ struct AttnBwdArgs {
   const uint8_t* tile_grp;
   const uint8_t* padding;
   const uint8_t* kt_class;
+  const uint8_t* skip_ok;  // [B] or nullptr: all-padded query tiles of this sample are left out (mca_query_skip_flags)
   const float* lse;     // [B,H,N]
   const float* delta;   // [B,H,N]
   const float* ucorr;   // [B, H*64]
@@ -203,7 +204,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           const int b = bh / a.H, h = bh % a.H;
           const mca_attn_qtile KT = a.k_tiles_q[kt];
           const int cls = a.kt_class[static_cast<long long>(b) * a.n_kt + kt];
-          if (cls == 2 || KT.kt_cnt == 0) {
+          // the query tiles that attend this key tile; varlen: tiles whose rows are all padded are left out when the
+          // sample's flag allows it (their dQ rows stay zero, they add nothing to dK / dV)
+          int cnt = 0;
+          if (cls != 2) {
+            const bool skip = a.skip_ok != nullptr && a.skip_ok[b] != 0;
+            for (int i0 = 0; i0 < KT.kt_cnt; i0 += 32) {
+              const int i = i0 + lane;
+              bool keep = false;
+              int2 v = make_int2(0, 0);
+              if (i < KT.kt_cnt) {
+                const int tid = a.qt_list[KT.kt_off + i].tile;
+                const mca_attn_tile Q = a.q_tiles[tid];
+                v = make_int2(Q.start, Q.len);
+                keep = !(skip && a.kt_class[static_cast<long long>(b) * a.n_kt + tid] == 2);
+              }
+              const uint32_t m = __ballot_sync(0xffffffffu, keep);
+              if (keep) s_qt[slot][cnt + __popc(m & ((1u << lane) - 1u))] = v;
+              cnt += __popc(m);
+            }
+          }
+          if (cnt == 0) {
             const float* uc = a.ucorr + static_cast<long long>(b) * HD + h * AB_DH;
             for (int i = lane; i < KT.len * 16; i += 32) {  // 16 chunks of 8 bf16 per row: 8 of dK, 8 of dV
               const int row = i >> 4, ch = i & 15;
@@ -219,13 +240,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             }
             continue;
           }
-          for (int i = lane; i < KT.kt_cnt; i += 32) {
-            const mca_attn_tile Q = a.q_tiles[a.qt_list[KT.kt_off + i].tile];
-            s_qt[slot][i] = make_int2(Q.start, Q.len);
-          }
           __syncwarp();
           if (lane == 0) {
-            s_item[slot] = AbItem{KT.kt_cnt, b, h, kt, KT.start, KT.len, a.tile_grp[kt], cls};
+            s_item[slot] = AbItem{cnt, b, h, kt, KT.start, KT.len, a.tile_grp[kt], cls};
             mbar_arrive(&item_full[slot]);
           }
           __syncwarp();
@@ -762,8 +779,9 @@ using namespace mca;
 extern "C" int mca_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                             const mca_attn_qtile* k_tiles_q, int n_kt, const mca_attn_ref* qt_list,
                             const mca_attn_tile* q_tiles, int n_qt, const uint32_t* rowbits, const uint8_t* keygrp,
-                            const uint8_t* tile_grp, const uint8_t* padding, const uint8_t* kt_class, float* delta,
-                            float* ucorr, float* dq_accum, void* dqkv, int B, int N, int H, void* stream_) {
+                            const uint8_t* tile_grp, const uint8_t* padding, const uint8_t* kt_class,
+                            const uint8_t* skip_ok, float* delta, float* ucorr, float* dq_accum, void* dqkv, int B, int N,
+                            int H, void* stream_) {
   if (B <= 0 || N <= 0 || H * AB_DH != 512 || n_qt <= 0 || n_qt > AB_MAX_ITERS) return MCA_ERR_SHAPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int HD = H * AB_DH;
@@ -786,7 +804,7 @@ extern "C" int mca_attn_bwd(const void* qkv, const void* out, const void* dout, 
   attn_bwd_prep_kernel<<<dim3((N + PREP_ROWS - 1) / PREP_ROWS, B), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta, ucorr, B, N, H);
   const int n_items = B * H * n_kt;  // item index = key tile (slow) x (sample, head)
-  AttnBwdArgs a{k_tiles_q, qt_list, q_tiles, rowbits, keygrp, tile_grp, padding, kt_class, lse, delta, ucorr,
+  AttnBwdArgs a{k_tiles_q, qt_list, q_tiles, rowbits, keygrp, tile_grp, padding, kt_class, skip_ok, lse, delta, ucorr,
                 reinterpret_cast<__nv_bfloat16*>(dqkv), N, H, n_kt, n_items, B * H};
   const int grid = n_items < num_sms() ? n_items : num_sms();  // persistent: one CTA per SM pulls from the queue
   attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tm_qkv, tm_do, tm_dq, a);

@@ -57,6 +57,8 @@ struct AttnFwdArgs {
   const uint8_t* tile_grp;   // [n_kt] key group of the tile, 255 = mixed
   const uint8_t* kt_class;   // [B, n_kt]
   const uint32_t* kt_live;   // [B, n_kt, 4] live-key bits
+  const uint8_t* padding;    // [B, N] (only read when skip_ok != nullptr)
+  const uint8_t* skip_ok;    // [B] or nullptr: query tiles of this sample whose rows are ALL padded need no scores
   const float* vmean;        // [B, H*64]
   __nv_bfloat16* out;        // [B*N, H*64]
   float* lse;                // [B, H, N]
@@ -354,6 +356,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a)
         tma_load_2d(sQ + slot * AT_TILE_BYTES, &tm_qkv, &q_full[slot], h * AT_DH, static_cast<int>(row0 + Q.start));
       }
       __syncwarp();
+      // varlen: a query tile whose rows are all padded produces rows nobody reads when the sample's flag allows it
+      // (mca_query_skip_flags): it is staged with an empty schedule (its rows get the fully-masked value, LSE = +inf)
+      bool dead_q = false;
+      if (a.skip_ok != nullptr && a.skip_ok[b] != 0) {
+        const uint8_t* pr = a.padding + row0 + Q.start;
+        bool live = false;
+        for (int i = lane; i < Q.len; i += 32) live |= pr[i] == 0;
+        dead_q = !__any_sync(0xffffffffu, live);
+      }
       // stage the item's schedule: the visited key tiles that hold at least one live key for this sample, in order
       AtSched* sched = sched_all + slot * AT_MAX_KT;
       const uint8_t* cls = a.kt_class + static_cast<long long>(b) * a.n_kt;
@@ -365,7 +376,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a)
         if (t < Q.kt_cnt) {
           const mca_attn_ref ref = a.kt_list[Q.kt_off + t];
           const int c = cls[ref.tile];
-          keep = c != 2;
+          keep = c != 2 && !dead_q;
           const mca_attn_tile K = a.k_tiles[ref.tile];
           const int grp = a.tile_grp[ref.tile];
           const bool masked = (ref.flags & 1) || c == 1 || K.len < AT_BN || grp == 255;
@@ -535,9 +546,10 @@ using namespace mca;
 extern "C" int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int n_qt, const mca_attn_ref* kt_list,
                             const mca_attn_tile* k_tiles, int n_kt, const uint32_t* rowbits, const uint8_t* keygrp,
                             const uint8_t* tile_grp, const uint8_t* kt_class, const uint32_t* kt_live,
-                            const int* any_absent, float* vmean, void* out, float* lse, int B, int N, int H,
-                            void* stream_) {
+                            const uint8_t* padding, const uint8_t* skip_ok, const int* any_absent, float* vmean, void* out,
+                            float* lse, int B, int N, int H, void* stream_) {
   if (B <= 0 || N <= 0 || H <= 0 || n_qt <= 0 || n_kt > AT_MAX_KT) return MCA_ERR_SHAPE;
+  if (skip_ok != nullptr && padding == nullptr) return MCA_ERR_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int ld = 3 * H * AT_DH;
   CUtensorMap tm;
@@ -555,7 +567,7 @@ extern "C" int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int 
   vmean_kernel<<<gv, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ld, 2 * H * AT_DH, H * AT_DH, N,
                                        any_absent, vmean);
   const int n_items = B * H * n_qt;  // item index = query tile (slow, heaviest first) x (sample, head)
-  AttnFwdArgs a{q_tiles, kt_list, k_tiles, rowbits, keygrp, tile_grp, kt_class, kt_live, vmean,
+  AttnFwdArgs a{q_tiles, kt_list, k_tiles, rowbits, keygrp, tile_grp, kt_class, kt_live, padding, skip_ok, vmean,
                 reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, n_kt, n_items, B * H};
   const int grid = n_items < 2 * num_sms() ? n_items : 2 * num_sms();  // persistent: two CTAs per SM pull from the queue
   attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, a);

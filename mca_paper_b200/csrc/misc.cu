@@ -321,6 +321,26 @@ extern "C" int mca_batchsum_rows(const float* src, float* out, int F, int d, int
   return check_launch();
 }
 
+__global__ void query_skip_flags_kernel(const uint8_t* __restrict__ present, int n_blk, int n_mod, int B, int mode,
+                                        uint8_t* __restrict__ skip_ok) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  uint8_t ok = mode == 2 ? 1 : 0;
+  if (mode == 1) {
+    ok = 1;
+    for (int m = 0; m < n_mod; ++m) ok &= present[b * n_blk + m] != 0 ? 1 : 0;
+  }
+  skip_ok[b] = ok;
+}
+
+extern "C" int mca_query_skip_flags(const uint8_t* present, int n_blk, int n_mod, int B, int mode, uint8_t* skip_ok,
+                                    void* stream) {
+  if (B <= 0 || n_mod <= 0 || n_mod > n_blk || mode < 0 || mode > 2) return MCA_ERR_SHAPE;
+  query_skip_flags_kernel<<<(B + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(present, n_blk, n_mod, B, mode,
+                                                                                          skip_ok);
+  return check_launch();
+}
+
 extern "C" int mca_cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows,
                                  int cols, void* stream) {
   if (rows <= 0 || (cols % 4) != 0) return MCA_ERR_SHAPE;

@@ -120,8 +120,26 @@ dp_reduce_shard_kernel(const float* const* __restrict__ grads_peers, const float
   __shared__ float red[8];
   float acc = 0.f;
   const long long n4 = n / 4;  // shards are multiples of 4 elements
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (grads_mc != nullptr) {
+    // four independent in-switch reductions in flight per thread (a multimem.ld_reduce round trip crosses the NVSwitch)
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(t[u].x), "=f"(t[u].y), "=f"(t[u].z), "=f"(t[u].w)
+                     : "l"(grads_mc + off + 4 * (i + u * stride))
+                     : "memory");
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        reinterpret_cast<float4*>(grads_local + off)[i + u * stride] = t[u];
+        acc += t[u].x * t[u].x + t[u].y * t[u].y + t[u].z * t[u].z + t[u].w * t[u].w;
+      }
+    }
+  }
+  for (; i < n4; i += stride) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (grads_mc != nullptr) {
       // NVSwitch in-fabric reduction: ONE load through the multicast address returns the sum over every rank's copy

@@ -58,6 +58,11 @@ class Engine:
         self.parallel_encoders = os.environ.get("MCA_PARALLEL_ENCODERS", "1") != "0"
         self.precision = "bf16"
         self._xws = None
+        # varlen query skipping in the attention kernels (include/mca_b200.h, mca_query_skip_flags): "exact" (default) skips
+        # all-padded query tiles only where no result can change, "fast" skips them in every sample, "off" never
+        self.varlen = os.environ.get("MCA_VARLEN", "exact").lower()
+        if self.varlen not in ("exact", "fast", "off") or self.eao:
+            self.varlen = "off"   # (EAO replicates modalities per pass: its masks are per block, not per modality)
         if os.environ.get("MCA_PRECISION", "bf16").lower() in ("fp32", "f32", "float32"):
             self.precision = "fp32"
 
@@ -349,6 +354,7 @@ class Engine:
         ws["live_idx"], ws["cu_live"] = i32(B, N), i32(B * n_blk + 1)
         ws["kt_class"], ws["any_absent"], ws["nonfinite"] = u8(B, self.n_kt), i32(1), i32(1)
         ws["kt_live"] = i32(B, self.n_kt, 4)
+        ws["skip_ok"] = u8(B)     # varlen query skipping flags (mca_query_skip_flags)
         # encoders
         ws["enc"] = {}
         for name, enc in zip(self.plan.names, self.model.encoder_specs):
@@ -520,6 +526,9 @@ class Engine:
              ctypes.cast(lens, ctypes.c_void_p), n, self.B, self.N, P(self.kt_start), P(self.kt_len), self.n_kt,
              P(ws["padding"]), P(ws["pad_mod"]), P(ws["present"]), P(ws["live_count"]), P(ws["live_idx"]),
              P(ws["cu_live"]), P(ws["kt_class"]), P(ws["kt_live"]), P(ws["any_absent"]), S())
+        if self.varlen != "off":
+            call("mca_query_skip_flags", P(ws["present"]), n, len(pl.names), self.B, 1 if self.varlen == "exact" else 2,
+                 P(ws["skip_ok"]), S())
 
     def _patchify(self, name, enc, values):
         """values [B,H,W] -> e['ptok'] [B*L, p1*p2] and the all-pad mask e['mask'] [B,L] (encoders.py:243-246,273)."""
@@ -705,11 +714,22 @@ class Engine:
             call("mca_dropout_rows", P(rows32), self.B, enc["max_tokens"], D, self.N, self.plan.offsets[i], p,
                  (torch.initial_seed() + 977 * i) & 0xFFFFFFFFFFFFFFFF, P(self.ws["drop_ctr"]), S())
 
+    def _skip_ok(self):
+        return self.ws["skip_ok"] if self.varlen != "off" else None
+
+    def set_varlen(self, mode: str):
+        """"exact" / "fast" / "off": which all-padded query tiles the attention kernels leave out (mca_query_skip_flags)."""
+        if mode not in ("exact", "fast", "off"):
+            raise ValueError(f"varlen mode {mode!r}: expected 'exact', 'fast' or 'off'")
+        if self.eao and mode != "off":
+            raise NotImplementedError("varlen query skipping covers the MCA / MMA models")
+        self.varlen = mode
+
     def attention_fwd(self, qkv, out, lse):
         ws = self.ws
         call("mca_attn_fwd", P(qkv), P(self.q_tiles), int(self.q_tiles.shape[0]), P(self.kt_list), P(self.k_tiles),
              self.n_kt, P(self.rowbits), P(self.keygrp), P(self.tile_grp), P(ws["kt_class"]), P(ws["kt_live"]),
-             P(ws["any_absent"]), P(ws["vmean"]), P(out), P(lse), self.B, self.N, self.H, S())
+             P(ws["padding"]), P(self._skip_ok()), P(ws["any_absent"]), P(ws["vmean"]), P(out), P(lse), self.B, self.N, self.H, S())
 
     def trunk_forward(self, batch):
         """encoders -> depth x [LN, QKV, attention, out-proj(+res), LN, FF1(GEGLU), FF2(+res)] -> LN -> pooling."""
@@ -888,7 +908,7 @@ class Engine:
         ws = self.ws
         call("mca_attn_bwd", P(ws["qkv"][l]), P(ws["ao"][l]), P(ws["dattn"]), P(ws["lse"][l]), P(self.k_tiles_q),
              self.n_kt, P(self.qt_list), P(self.k_tiles), int(self.q_tiles.shape[0]), P(self.rowbits), P(self.keygrp),
-             P(self.tile_grp), P(ws["padding"]), P(ws["kt_class"]), P(ws["delta"]), P(ws["ucorr"]), P(ws["dq_acc"]),
+             P(self.tile_grp), P(ws["padding"]), P(ws["kt_class"]), P(self._skip_ok()), P(ws["delta"]), P(ws["ucorr"]), P(ws["dq_acc"]),
              P(ws["dqkv"]),
              self.B, self.N, self.H, S())
 

@@ -41,8 +41,9 @@ _SIGS = {
     "mca_broadcast_rows": [VP, VP, I32, I32, I32, I32, I32, VP],
     "mca_batchsum_rows": [VP, VP, I32, I32, I32, I32, I32, I32, VP],
     "mca_cast_f32_bf16": [VP, I64, VP, I64, I64, I32, VP],
-    "mca_attn_fwd": [VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
-    "mca_attn_bwd": [VP, VP, VP, VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
+    "mca_attn_fwd": [VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
+    "mca_attn_bwd": [VP, VP, VP, VP, VP, I32, VP, VP, I32, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, VP],
+    "mca_query_skip_flags": [VP, I32, I32, I32, I32, VP, VP],
     "mca_pool_attn_fwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
     "mca_pool_attn_bwd": [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, I32, I32, VP],
     "mca_small_gemm_f32": [VP, I64, I64, VP, I64, I64, VP, I64, VP, I64, I32, I32, I32, I32, F32, I32, VP],
@@ -78,6 +79,8 @@ _SIGS = {
     "mca_cross_entropy_fwd": [VP, I64, VP, I32, I32, F32, VP, VP, VP],
     "mca_cross_entropy_bwd": [VP, I64, VP, I32, I32, F32, VP, VP, VP, VP, VP, VP],
     "mca_attn_probs": [VP, VP, VP, VP, VP, I32, I32, I32, VP, VP],
+    "mca_probe_epoch": [VP, VP, VP, I32, I32, I32, I32, I32, VP, VP, VP, VP, VP, VP, VP],
+    "mca_probe_pcc": [VP, VP, I64, VP, VP],
     "mca_x_split_f32": [VP, I64, VP, I64, I32, I32, I32, VP],
     "mca_x_pack_weights_split": [VP, VP, VP, I32, VP],
     "mca_x_layernorm_in_split": [VP, VP, VP, VP, VP, I32, I32, I64, VP],

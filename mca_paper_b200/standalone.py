@@ -273,7 +273,7 @@ class _Attention(torch.autograd.Function):
         y = torch.empty(M, D, device=dev, dtype=torch.float32)
         ops.gemm(x16, 0, pk.W("qkv"), 0, M, 3 * D, D, _lib.EPI_BF16, qkv)
         call("mca_attn_fwd", P(qkv), P(tab.q_tiles), int(tab.q_tiles.shape[0]), P(tab.kt_list), P(tab.k_tiles), tab.n_kt,
-             P(tab.rowbits), P(tab.keygrp), P(tab.tile_grp), P(tab.kt_class), P(tab.kt_live), P(tab.any_absent),
+             P(tab.rowbits), P(tab.keygrp), P(tab.tile_grp), P(tab.kt_class), P(tab.kt_live), None, None, P(tab.any_absent),
              P(tab.vmean), P(ao), P(lse), B, N, H, S())
         ops.gemm(ao, 0, pk.W("out"), 0, M, D, D, _lib.EPI_F32, y)
         probs = None
@@ -304,7 +304,7 @@ class _Attention(torch.autograd.Function):
         dqkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
         call("mca_attn_bwd", P(qkv), P(ao), P(dattn), P(lse), P(tab.k_tiles_q), tab.n_kt, P(tab.qt_list), P(tab.k_tiles),
              int(tab.q_tiles.shape[0]), P(tab.rowbits), P(tab.keygrp), P(tab.tile_grp), P(padding), P(kt_class),
-             P(delta), P(ucorr), P(dq_acc), P(dqkv), B, N, H, S())
+             None, P(delta), P(ucorr), P(dq_acc), P(dqkv), B, N, H, S())
         dx = torch.empty(M, D, device=dev, dtype=torch.float32)
         ops.gemm(dqkv, 0, pk.W("qkv"), 1, M, D, 3 * D, _lib.EPI_F32, dx)
         pk.dw("qkv", dqkv, x16, M)

@@ -25,7 +25,7 @@ ws = eng.ws
 ws["dattn"].copy_(do)
 call("mca_attn_bwd", P(qkv), P(out), P(ws["dattn"]), P(lse), P(eng.k_tiles_q), eng.n_kt, P(eng.qt_list), P(eng.k_tiles),
      int(eng.q_tiles.shape[0]), P(eng.rowbits), P(eng.keygrp), P(eng.tile_grp), P(ws["padding"]), P(ws["kt_class"]),
-     P(ws["delta"]), P(ws["ucorr"]), P(ws["dq_acc"]), P(ws["dqkv"]), B, N, H, torch.cuda.current_stream().cuda_stream)
+     None, P(ws["delta"]), P(ws["ucorr"]), P(ws["dq_acc"]), P(ws["dqkv"]), B, N, H, torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 d = ws["dqkv"].float()
 x = qkv.float().view(B, N, 3, H, 64)
