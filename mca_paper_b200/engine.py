@@ -771,9 +771,14 @@ class Engine:
                  P(ws["pooled"]), P(ws["pool_cnt"]), P(ws["pool_scratch"]), S())
             return ws["pooled"]
         # attention pooling on the final-normed tokens (model.py:470-473)
-        ops.gemm(ws["xf_16"], 0, self.W("attn_pool.kv"), 0, M, 2 * D, D, _lib.EPI_BF16, ws["kvp"])
         rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
-        ops.small_gemm(rt, D, 1, wq, D, 1, ws["qp"], D, self.R, D, D, alpha=DH ** -0.5)
+        main, side = self._pool_side()
+        with torch.cuda.stream(side):   # the pooled queries only depend on parameters: under the K/V projection
+            ops.small_gemm(rt, D, 1, wq, D, 1, ws["qp"], D, self.R, D, D, alpha=DH ** -0.5)
+        ops.gemm(ws["xf_16"], 0, self.W("attn_pool.kv"), 0, M, 2 * D, D, _lib.EPI_BF16, ws["kvp"])
+        if side is not main:
+            self._pool_ev[3].record(side)
+            main.wait_event(self._pool_ev[3])
         call("mca_pool_attn_fwd", P(ws["qp"]), P(ws["kvp"]), P(ws["padding"]), P(self.keygrp), P(self.pool_rowbits),
              P(ws["probs"]), P(ws["fm"]), P(ws["po"]), self.B, self.H, self.R, self.N, S())
         # pooled[b, r] = po[b, r] Wo^T + return_tokens[r]
@@ -861,18 +866,47 @@ class Engine:
         rt, wq, wo = self.pview("return_tokens"), self.pview("attn_pool.to_q.weight"), self.pview("attn_pool.to_out.weight")
         dp2 = dpooled.reshape(B * R, D)
         po2 = ws["po"].view(B * R, D)
-        # pooled = po Wo^T + rt
-        call("mca_batchsum_rows", P(dp2), P(self.gview("return_tokens")), R, D, B, R, 0, 1, S())
-        ops.small_gemm(dp2, 1, D, po2, 1, D, self.gview("attn_pool.to_out.weight"), D, D, D, B * R)       # dWo = dp^T po
+        # pooled = po Wo^T + rt.  The R-row products are latency-bound (13 us each whatever their size): the ones off the
+        # critical path dpo -> pool backward -> dxf run on a side stream (a graph branch), joined before mca_unpack_grads.
+        main, side = self._pool_side()
+        sc = DH ** -0.5
+        with torch.cuda.stream(side):
+            call("mca_batchsum_rows", P(dp2), P(self.gview("return_tokens")), R, D, B, R, 0, 1, S())
+            ops.small_gemm(dp2, 1, D, po2, 1, D, self.gview("attn_pool.to_out.weight"), D, D, D, B * R)   # dWo = dp^T po
         ops.small_gemm(dp2, D, 1, wo, 1, D, ws["dpo"].view(B * R, D), D, B * R, D, D)                        # dpo = dp Wo
         call("mca_pool_attn_bwd", P(ws["dpo"]), P(ws["qp"]), P(ws["kvp"]), P(ws["probs"]), P(ws["fm"]), P(ws["pool_ds"]),
              P(ws["dkvp"]), P(ws["dqp"]), B, H, R, N, S())
-        sc = DH ** -0.5
-        ops.small_gemm(ws["dqp"], 1, D, rt, 1, D, self.gview("attn_pool.to_q.weight"), D, D, D, R, alpha=sc)  # dWq
-        ops.small_gemm(ws["dqp"], D, 1, wq, 1, D, self.gview("return_tokens"), D, R, D, D, alpha=sc, accumulate=True)
+        if side is not main:
+            self._pool_ev[1].record(main)
+            side.wait_event(self._pool_ev[1])
+        with torch.cuda.stream(side):
+            ops.small_gemm(ws["dqp"], 1, D, rt, 1, D, self.gview("attn_pool.to_q.weight"), D, D, D, R, alpha=sc)  # dWq
+            ops.small_gemm(ws["dqp"], D, 1, wq, 1, D, self.gview("return_tokens"), D, R, D, D, alpha=sc, accumulate=True)
+        if side is not main:
+            self._pool_ev[2].record(side)
+            self._pool_pending = True
         # through the K/V projection and the final LayerNorm
         ops.gemm(ws["dkvp"], 0, self.W("attn_pool.kv"), 1, M, D, 2 * D, _lib.EPI_F32, ws["dxf"])
         self._dw("attn_pool.kv", ws["dkvp"], ws["xf_16"], 2 * D, D, M)
+
+    def _pool_side(self):
+        """(current stream, side stream forked from it) for the small pooling products; the same stream twice when
+        MCA_PARALLEL_ENCODERS=0."""
+        main = torch.cuda.current_stream()
+        if not self.parallel_encoders:
+            return main, main
+        if getattr(self, "_pool_stream", None) is None:
+            self._pool_stream = torch.cuda.Stream(device=self.device)
+            self._pool_ev = [torch.cuda.Event() for _ in range(4)]
+            self._pool_pending = False
+        self._pool_ev[0].record(main)
+        self._pool_stream.wait_event(self._pool_ev[0])
+        return main, self._pool_stream
+
+    def _pool_join(self):
+        if getattr(self, "_pool_pending", False):
+            torch.cuda.current_stream().wait_event(self._pool_ev[2])
+            self._pool_pending = False
 
     def _layers_backward(self, dx, dx_alt):
         ws, M, IP = self.ws, self.M, self.IP
@@ -902,6 +936,7 @@ class Engine:
             for dst, src, L in self.plan.replicas:
                 dv[:, src:src + L].add_(dv[:, dst:dst + L])
         self.encode_backward(dx)
+        self._pool_join()
         call("mca_unpack_grads", P(self.flat_grad), P(self.garena), P(self.unpack_descs), self.n_desc, S())
 
     def attention_bwd(self, l):
