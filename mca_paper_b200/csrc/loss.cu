@@ -218,15 +218,19 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ w, float* __restrict__ dpo
     if (lane == 0) atomicAdd(&s_ds, ds);
   }
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(dscale, s_ds);
+  if (threadIdx.x == 0 && blockIdx.z == 0) atomicAdd(dscale, s_ds);
   // embedding gradients, thread = embedding column: d query_i += T sum_j dl[i][j] key_j ; d key_j += T sum_i dl[i][j] query_i.
-  // Every gathered key row is read once per CTA (coalesced across the threads).
+  // Every gathered key row is read once per CTA (coalesced across the threads).  Under data parallelism the gathered rows
+  // are dealt to gridDim.z CTAs per (pair, direction) — each recomputes the (cheap) logits and walks its own slice of keys:
+  // the serial walk over all G*B rows was what grew with the world size (62 us at G = 8).
   const int rq = dir == 0 ? p.a_row : p.b_row, rk = dir == 0 ? p.b_row : p.a_row;
+  const int jchunk = (a.GB + static_cast<int>(gridDim.z) - 1) / static_cast<int>(gridDim.z);
+  const int j0 = static_cast<int>(blockIdx.z) * jchunk, j1 = min(a.GB, j0 + jchunk);
   for (int c = threadIdx.x; c < a.d; c += blockDim.x) {
     float qreg[LOSS_MAXB], dq[LOSS_MAXB];
 #pragma unroll
     for (int i = 0; i < LOSS_MAXB; ++i) qreg[i] = i < a.B ? qs[i * a.d + c] : 0.f, dq[i] = 0.f;
-    for (int j = 0; j < a.GB; ++j) {
+    for (int j = j0; j < j1; ++j) {
       const float k = pooled_row(a, j, rk)[c];
       float dk = 0.f;
 #pragma unroll
@@ -352,7 +356,8 @@ extern "C" int mca_contrastive_allpairs_bwd(const float* pooled_all, const uint8
     attr = true;
   }
   LossArgs a{pooled_all, present, plan_dev, logit_scale, B, GB, R, d, n_mod, rank, n_pairs};
-  loss_bwd_kernel<<<dim3(n_pairs, 2), LOSS_THREADS, smem, stream>>>(a, w, dpooled_all, dscale);
+  const int zsplit = GB / B > 1 ? (GB / B > 8 ? 8 : GB / B) : 1;  // one slice of gathered rows per rank (at most 8)
+  loss_bwd_kernel<<<dim3(n_pairs, 2, zsplit), LOSS_THREADS, smem, stream>>>(a, w, dpooled_all, dscale);
   return check_launch();
 }
 

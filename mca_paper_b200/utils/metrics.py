@@ -55,14 +55,47 @@ def wang_loss(x, y, lam=1.0, alpha=2, t=2):
     return lalign(x, y, alpha) + lam * (lunif(x, t) + lunif(y, t)) / 2
 
 
+def gather_cat(chunks, dim0_width=None):
+    """torchmetrics' `dist_reduce_fx="cat"` (utils/metrics.py:44-45,64): the state a metric computes on is the
+    concatenation, in rank order, of every rank's accumulated rows.  Outside a process group (or with one rank) it is the
+    local concatenation.  Ranks may hold different numbers of rows: the counts are exchanged first and the rows padded to
+    the longest for one all_gather."""
+    local = torch.cat(list(chunks), 0) if len(chunks) else None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        if local is None:
+            raise ValueError("metric has no accumulated state")
+        return local
+    world = dist.get_world_size()
+    if local is None:
+        raise ValueError("metric has no accumulated state on this rank")
+    n = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    mx = max(counts)
+    padded = local.new_zeros((mx,) + tuple(local.shape[1:]))
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous())
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
+
+
 class _Accumulator:
     """The slice of the torchmetrics.Metric protocol the reference scripts use: update(), compute(), reset() and
-    calling the object on one batch (= update + compute on that batch alone, state kept)."""
+    calling the object on one batch (= update + compute on that batch alone, state kept).  compute() evaluates on the
+    rows of EVERY rank when a process group is initialised (the reference's states are `dist_reduce_fx="cat"`); the
+    per-batch value of a call is local, as torchmetrics' forward is with dist_sync_on_step=False."""
 
     _states = ()
 
     def __init__(self):
+        self._sync = True
         self.reset()
+
+    def _state(self, name):
+        chunks = getattr(self, name)
+        return gather_cat(chunks) if self._sync else torch.cat(chunks, 0)
 
     def reset(self):
         for s in self._states:
@@ -76,7 +109,11 @@ class _Accumulator:
         for s in self._states:
             setattr(self, s, [])
         self.update(*args)
-        val = self.compute()
+        self._sync = False
+        try:
+            val = self.compute()
+        finally:
+            self._sync = True
         for s in self._states:
             setattr(self, s, keep[s] + getattr(self, s))
         return val
@@ -98,7 +135,7 @@ class Alignment(_Accumulator):
             raise ValueError("preds and target must have the same shape")
 
     def compute(self, norm=False):
-        return lalign(torch.cat(self.preds, 0), torch.cat(self.target, 0), self.alpha, norm)
+        return lalign(self._state("preds"), self._state("target"), self.alpha, norm)
 
 
 class Uniformity(_Accumulator):
@@ -113,7 +150,7 @@ class Uniformity(_Accumulator):
         self.preds.append(preds)
 
     def compute(self, norm=False):
-        return lunif(torch.cat(self.preds, 0), self.t, norm)
+        return lunif(self._state("preds"), self.t, norm)
 
 
 def retrieval_ranks(embeddings, targets, indices):

@@ -284,6 +284,52 @@ def test_graph_trainer_applies_one_update_per_step_call():
     assert abs(lg - le) <= 2e-3 * abs(le) and ef < 1e-3 and em < 1e-2, (lg, le, ef, em)   # atomics order only
 
 
+def test_pipelined_staging_keeps_batches_apart():
+    """The host runs ahead of the device (no step synchronises): alternating two DIFFERENT batches through the pinned
+    staging sets — plain step(), the prefetch / step_from_slot pipeline, and step_device on device-resident batches — must
+    give, step by step, the losses of the same sequence run with a full synchronisation after every step (a pinned
+    buffer rewritten before its H2D copy had run would mix the two batches)."""
+    cfg = C.tiny_config("cmu", fcl=True)
+    kw = C.get_model_config(cfg)
+    batches = [S.make_batch(cfg, seed=11, variant="dropout_ragged"), S.make_batch(cfg, seed=12, variant="full")]
+    seq = [0, 1, 1, 0, 1, 0, 0, 1]
+
+    def run(mode):
+        torch.manual_seed(0)
+        model = MCA(**kw).to(dev)
+        tr = Trainer(model, lr=1e-3, clip=2.0, schedule="constant", use_graphs=True)
+        tr.step(batches[0])                       # capture (state restored afterwards), buffers allocated
+        torch.cuda.synchronize()
+        out = []
+        if mode == "sync":
+            for i in seq:
+                out.append(tr.step(batches[i]).clone())
+                torch.cuda.synchronize()
+        elif mode == "async":
+            for i in seq:
+                out.append(tr.step(batches[i]).clone())
+        elif mode == "pipeline":
+            tr._ensure_pipeline()
+            tr.prefetch(0, batches[seq[0]])
+            for k, i in enumerate(seq):
+                if k + 1 < len(seq):
+                    tr.prefetch((k + 1) & 1, batches[seq[k + 1]])
+                out.append(tr.step_from_slot(k & 1).clone())
+        else:
+            devb = [S.batch_to(b, dev) for b in batches]
+            for i in seq:
+                out.append(tr.step_device(devb[i]).clone())
+        torch.cuda.synchronize()
+        return [float(o[0]) for o in out]
+
+    want = run("sync")
+    assert len(set(round(w, 4) for w in want)) > 2     # the two batches do give different losses
+    for mode in ("async", "pipeline", "device"):
+        got = run(mode)
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 5e-3 * abs(b), (mode, got, want)   # run-to-run noise of the bf16 step, not a batch mix-up
+
+
 def test_patch_encoder_dropout_training_mode():
     """PatchEncoder's nn.Dropout (encoders.py:274): active only in training mode, keeps ~1-p of the elements scaled by
     1/(1-p), draws a new mask every forward, and the backward applies the SAME mask (dropped elements get no gradient:
