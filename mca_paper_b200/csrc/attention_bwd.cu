@@ -140,6 +140,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HD = a.H * AB_DH;
+  pdl_launch_dependents();
 
   if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -172,6 +173,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();  // set-up ran under the predecessor's tail (PDL); nothing above touches global memory
   // columns: [0,128) S^T (queries 0..127), [128,256) dP^T, [256,288) P^T (16) | dS^T (16) of half 0's quarter in flight,
   //          [288,320) the same for half 1,
   //          [320,384) dV, [384,448) dK, [448,512) dQ
@@ -722,6 +724,7 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16*
                      const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ ucorr, int B, int N,
                      int H) {
   __shared__ float s_part[8][512];
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int HD = H * AB_DH;  // 512: each lane owns 16 consecutive columns, 4 lanes per head
@@ -807,7 +810,8 @@ extern "C" int mca_attn_bwd(const void* qkv, const void* out, const void* dout, 
   AttnBwdArgs a{k_tiles_q, qt_list, q_tiles, rowbits, keygrp, tile_grp, padding, kt_class, skip_ok, lse, delta, ucorr,
                 reinterpret_cast<__nv_bfloat16*>(dqkv), N, H, n_kt, n_items, B * H};
   const int grid = n_items < num_sms() ? n_items : num_sms();  // persistent: one CTA per SM pulls from the queue
-  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tm_qkv, tm_do, tm_dq, a);
+  if (launch_kernel(attn_bwd_kernel, dim3(grid), dim3(AB_THREADS), AB_SMEM, stream, 1, tm_qkv, tm_do, tm_dq, a) != cudaSuccess)
+    return MCA_ERR_CUDA;
   if (cudaGetLastError() != cudaSuccess) return MCA_ERR_CUDA;
   // dQ: fp32 accumulator -> bf16 first column block of dqkv
   return mca_cast_f32_bf16(dq_accum, HD, dqkv, 3 * HD, M, HD, stream_);

@@ -301,6 +301,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a)
   uint32_t* tmem_holder = &tmem_holder_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == AT_SOFT_WARPS && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -327,6 +328,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnFwdArgs a)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
+  pdl_wait();  // set-up ran under the predecessor's tail (PDL); nothing above touches global memory
 
   if (warp == AT_SOFT_WARPS) {
     // ===================== producer: work queue, schedule staging, TMA loads (whole warp loops) =====================
@@ -522,6 +524,7 @@ constexpr int VM_ROWS = 64;
 __global__ void __launch_bounds__(256)
 vmean_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int v_col0, int width, int N, const int* __restrict__ any_absent,
              float* __restrict__ vmean) {
+  pdl_launch_dependents();
   if (*any_absent == 0) return;
   const int b = blockIdx.y;
   const int n0 = blockIdx.x * VM_ROWS, n1 = min(N, n0 + VM_ROWS);
@@ -570,7 +573,7 @@ extern "C" int mca_attn_fwd(const void* qkv, const mca_attn_qtile* q_tiles, int 
   AttnFwdArgs a{q_tiles, kt_list, k_tiles, rowbits, keygrp, tile_grp, kt_class, kt_live, padding, skip_ok, vmean,
                 reinterpret_cast<__nv_bfloat16*>(out), lse, N, H, n_kt, n_items, B * H};
   const int grid = n_items < 2 * num_sms() ? n_items : 2 * num_sms();  // persistent: two CTAs per SM pull from the queue
-  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tm, a);
+  if (launch_kernel(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, 1, tm, a) != cudaSuccess) return MCA_ERR_CUDA;
   return check_launch();
 }
 

@@ -64,6 +64,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = base;
   uint8_t* sB = base + STAGES * A_BYTES;
@@ -105,6 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();  // set-up done under the predecessor's tail; from here on global memory is touched
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -362,7 +364,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tmA, tmB, tmO0, tmO1, tmAux, p);
+  if (launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM, stream, 1, tmA, tmB, tmO0, tmO1, tmAux, p) != cudaSuccess)
+    return MCA_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? MCA_OK : MCA_ERR_CUDA;
 }
 

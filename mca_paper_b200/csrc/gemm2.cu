@@ -119,6 +119,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2], aux_bar[EPI_WARPS];
   __shared__ uint32_t tmem_holder;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -153,6 +154,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  pdl_wait();  // set-up done under the predecessor's tail; from here on global memory is touched
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; whole warp loops, one elected lane issues) =====================
@@ -419,7 +421,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN) * p.k_splits;
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<2 * clusters, THREADS, SMEM, stream>>>(tmA, tmB, tmO0, tmO1, tmAux, p);
+  if (launch_kernel(kern, dim3(2 * clusters), dim3(THREADS), SMEM, stream, 1, tmA, tmB, tmO0, tmO1, tmAux, p) != cudaSuccess)
+    return MCA_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? MCA_OK : MCA_ERR_CUDA;
 }
 

@@ -171,6 +171,8 @@ __global__ void batchsum_rows_kernel(const float* __restrict__ src, float* __res
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
                                      long long ld_dst, long long rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4 = cols / 4;
   const long long n = rows * c4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -364,7 +366,8 @@ extern "C" int mca_query_skip_flags(const uint8_t* present, int n_blk, int n_mod
 extern "C" int mca_cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows,
                                  int cols, void* stream) {
   if (rows <= 0 || (cols % 4) != 0) return MCA_ERR_SHAPE;
-  cast_f32_bf16_kernel<<<148 * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols);
+  if (launch_kernel(cast_f32_bf16_kernel, dim3(148 * 4), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 2, src, ld_src,
+                    reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols) != cudaSuccess)
+    return MCA_ERR_CUDA;
   return check_launch();
 }

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(256)
 ln512_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float2* __restrict__ stats,
                  const uint8_t* __restrict__ pad, const float* __restrict__ pe, RowMap map, long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();  // launched with programmatic serialization: resident early, starts when the predecessor has completed
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -96,6 +98,8 @@ add_ln512_fwd_kernel(const float* __restrict__ xprev, const float2* __restrict__
                      const __nv_bfloat16* __restrict__ y16, float* __restrict__ xnew, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ out16, float2* __restrict__ stats,
                      long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -154,6 +158,8 @@ ln512_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__
                  const uint8_t* __restrict__ pad, RowMap map, long long rows) {
   __shared__ float sg[8][LN_D];
   __shared__ float sb[8][LN_D];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float ag[16], ab[16];
 #pragma unroll
@@ -346,8 +352,9 @@ extern "C" int mca_layernorm512_fwd(const float* x, const float* gamma, const fl
   if (pe != nullptr && seg_len <= 0) return MCA_ERR_ARG;
   RowMap map{seg_len, out_rows_per_b, out_row_off};
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  ln512_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, gamma, beta, y32, reinterpret_cast<__nv_bfloat16*>(y16), reinterpret_cast<float2*>(stats), pad, pe, map, rows);
+  if (launch_kernel(ln512_fwd_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 2, x, gamma, beta, y32,
+                    reinterpret_cast<__nv_bfloat16*>(y16), reinterpret_cast<float2*>(stats), pad, pe, map, rows) != cudaSuccess)
+    return MCA_ERR_CUDA;
   return check_launch();
 }
 
@@ -360,9 +367,10 @@ extern "C" int mca_layernorm512_bwd(const float* dy, const void* dy_delta_bf16, 
   long long want = (rows + 7) / 8;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-  ln512_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      dy, reinterpret_cast<const __nv_bfloat16*>(dy_delta_bf16), x, reinterpret_cast<const float2*>(stats), gamma, dx32,
-      reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta, pad, map, rows);
+  if (launch_kernel(ln512_bwd_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 2, dy,
+                    reinterpret_cast<const __nv_bfloat16*>(dy_delta_bf16), x, reinterpret_cast<const float2*>(stats), gamma, dx32,
+                    reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta, pad, map, rows) != cudaSuccess)
+    return MCA_ERR_CUDA;
   return check_launch();
 }
 
@@ -373,10 +381,11 @@ extern "C" int mca_add_layernorm512_fwd(const float* xprev, const float* stats_p
   if (xprev == nullptr || stats_prev == nullptr || gamma_prev == nullptr || y_bf16 == nullptr) return MCA_ERR_ARG;
   if (out_bf16 != nullptr && gamma == nullptr) return MCA_ERR_ARG;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  add_ln512_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      xprev, reinterpret_cast<const float2*>(stats_prev), gamma_prev, beta_prev,
-      reinterpret_cast<const __nv_bfloat16*>(y_bf16), xnew, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16),
-      reinterpret_cast<float2*>(stats), rows);
+  if (launch_kernel(add_ln512_fwd_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 2, xprev,
+                    reinterpret_cast<const float2*>(stats_prev), gamma_prev, beta_prev,
+                    reinterpret_cast<const __nv_bfloat16*>(y_bf16), xnew, gamma, beta,
+                    reinterpret_cast<__nv_bfloat16*>(out_bf16), reinterpret_cast<float2*>(stats), rows) != cudaSuccess)
+    return MCA_ERR_CUDA;
   return check_launch();
 }
 

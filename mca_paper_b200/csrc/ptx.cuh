@@ -355,4 +355,12 @@ __device__ __forceinline__ float gelu_exact_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor on the stream is still draining: it runs its set-up (barrier init, TMEM allocation, descriptor
+// prefetch), then pdl_wait() blocks until the predecessor grid has completed and its writes are visible — nothing before it
+// may touch global memory.  pdl_launch_dependents() (first instruction of a kernel) lets the successor's CTAs be scheduled as
+// soon as every CTA of this grid has started (or exited) and an SM has room.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace mca

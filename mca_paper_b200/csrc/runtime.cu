@@ -1,9 +1,20 @@
+#include <cstdlib>
 #include "runtime.h"
 
 #include <cudaTypedefs.h>
 #include <mutex>
 
 namespace mca {
+
+int pdl_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCA_PDL");
+    v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return v;
+}
+
 
 int num_sms() {
   static int cached = 0;
