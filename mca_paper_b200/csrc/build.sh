@@ -7,7 +7,7 @@ mkdir -p build
 pids=()
 for f in *.cu; do
   o="build/${f%.cu}.o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ ptx.cuh -nt "$o" ] || [ runtime.h -nt "$o" ] || [ ../../include/mca_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ ptx.cuh -nt "$o" ] || [ gemm_epilogue.cuh -nt "$o" ] || [ runtime.h -nt "$o" ] || [ ../../include/mca_b200.h -nt "$o" ]; then
     nvcc $FLAGS ${MCA_NVCC_EXTRA} -c "$f" -o "$o" &
     pids+=($!)
   fi

@@ -14,7 +14,7 @@ for spec in "tcga:--config TCGA_config1 --variant tcga" "d40:--config CMU_config
             "d40fast:--config CMU_config1_d40 --variant dropout_ragged --varlen fast" "mma:--config CMU_config1_z" \
             "eao:--config CMU_config1_EAO --steps 10"; do
   name=${spec%%:*}; flags=${spec#*:}
-  python bench.py --steps 20 --warmup 5 --no-cpu-baseline $flags > $OUT/bench_${TAG}_$name.json 2> $OUT/bench_${TAG}_$name.err
+  MCA_BENCH_TABLE=$OUT/kernel_table_${TAG}_$name.json python bench.py --steps 20 --warmup 5 --no-cpu-baseline $flags > $OUT/bench_${TAG}_$name.json 2> $OUT/bench_${TAG}_$name.err
   echo "bench $name rc=$?"; cut -c1-200 $OUT/bench_${TAG}_$name.json
 done
 python bench.py --mode infer --steps 30 --warmup 5 > $OUT/bench_${TAG}_infer.json 2> $OUT/bench_${TAG}_infer.err; echo "infer rc=$?"; cut -c1-200 $OUT/bench_${TAG}_infer.json
