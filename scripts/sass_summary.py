@@ -6,7 +6,7 @@ import collections, re, subprocess, sys
 lib = sys.argv[1] if len(sys.argv) > 1 else "mca_paper_b200/csrc/libmca_b200.so"
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 WATCH = ["UTCHMMA", "UTCQMMA", "UTCMMA", "UTCBAR", "UTCCP", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UBLKCP",
-         "SYNCS", "HMMA", "IMMA", "HGMMA", "MUFU.EX2", "MUFU", "FFMA", "FFMA2", "FMUL", "F2FP", "LDS", "STS", "LDG", "STG", "RED", "ATOM",
+         "SYNCS", "LDGMC", "PREEXIT", "ACQBULK", "HMMA", "IMMA", "HGMMA", "MUFU.EX2", "MUFU", "FFMA", "FFMA2", "FMUL", "F2FP", "LDS", "STS", "LDG", "STG", "RED", "ATOM",
          "BAR", "STL", "LDL", "USETMAXREG", "ELECT"]
 kern, counts, total = None, collections.OrderedDict(), {}
 for line in txt.splitlines():
@@ -24,7 +24,8 @@ for line in txt.splitlines():
             if op == w or op.startswith(w + "."):
                 counts[kern][w] += 1
 print(f"# {lib}: SASS opcode counts per kernel (sm_100a).  UTCHMMA = tcgen05.mma kind::f16, LDTM/STTM = tcgen05.ld/st, "
-      "UTMALDG/UTMASTG/UTMAREDG = TMA load/store/reduce, SYNCS = mbarrier ops, STL/LDL = local-memory spills")
+      "UTMALDG/UTMASTG/UTMAREDG = TMA load/store/reduce, SYNCS = mbarrier ops, LDGMC = multimem.ld_reduce (NVSwitch; multimem.st is a plain STG.E.128.STRONG.SYS to the multicast address), "
+      "PREEXIT / ACQBULK = griddepcontrol.launch_dependents / .wait (programmatic dependent launch), STL/LDL = local-memory spills")
 for k, c in counts.items():
     items = " ".join(f"{w}={c[w]}" for w in WATCH if c[w])
     print(f"{k[:70]:70s} instr={total[k]:6d}  {items}")
