@@ -4,7 +4,6 @@
 TAG=${1:-s8}; N=${2:-8}
 OUT=gpurun_out; mkdir -p $OUT
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 120 python -m pytest tests/test_gpu_varlen.py -m gpu -x -q > $OUT/pytest_varlen_$TAG.log 2>&1; echo "pytest varlen rc=$?"; tail -3 $OUT/pytest_varlen_$TAG.log | cut -c1-200
 timeout 300 $RUN --master-port 29701 scripts/gpu_dp_check.py tiny > $OUT/dp_check_${TAG}_n${N}_tiny.log 2>&1
 echo "dp_check tiny n$N rc=$?"; grep -E "^\[rank 0|DP CHECK|Error" $OUT/dp_check_${TAG}_n${N}_tiny.log | cut -c1-300 | head -10
 timeout 200 $RUN --master-port 29702 bench.py --gpus $N --steps 30 --warmup 5 > $OUT/bench_${TAG}_n$N.json 2> $OUT/bench_${TAG}_n$N.err
