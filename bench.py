@@ -32,6 +32,25 @@ sys.path.insert(0, ROOT)
 METRIC = "train samples/sec at CMU_config1 shape"
 UNIT = "samples/s"
 
+# stdout carries exactly ONE JSON line.  Libraries print to it behind Python's back (NCCL's "NCCL version ..." banner on the
+# first communicator, torchrun's OMP notice): file descriptor 1 is pointed at stderr for the whole run and the line is
+# written to a duplicate of the real stdout.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 def read_peaks():
     try:
@@ -165,7 +184,7 @@ def run_reference(args):
         "note": "reference cannot be installed (torchmultimodal/yacs/accelerate absent, no network); this arm times "
                 "oracle/mca_oracle.py, the CPU restatement pinned against the live reference (tests/golden)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_string(cfg_name: str, variant: str) -> str:
@@ -297,14 +316,14 @@ def run_infer(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     if rank == 0:
         h2d_bytes = sum(v.numel() * v.element_size() for d in host.values() for v in d.values())
-        print(json.dumps({
+        emit(({
             "metric": "embedding inference samples/sec (infer_accel_gpu.py forward incl. losses)", "unit": UNIT, "n_gpus": world,
             "value": world * eng.B * args.steps / (float(t[0]) * 1e-3), "steps": args.steps, "ms_per_step": float(t[0]) / args.steps,
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{name} MMA forward, eval/no_grad, B=8 per replica, variant={args.variant}",
                        "parallelism": f"{world} independent replicas (no collective)"},
             "e2e": {"value": world * eng.B * args.steps / (float(t[1]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": out_pin.numel() * 4, "ms_per_step": float(t[1]) / args.steps}}), flush=True)
+                    "d2h_bytes_per_step": out_pin.numel() * 4, "ms_per_step": float(t[1]) / args.steps}}))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -328,6 +347,7 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="infer = SURVEY.md §8d config 5: eval() forward + losses of infer_accel_gpu.py:97-111, replicas only")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.mode == "infer":
@@ -340,8 +360,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL's "NCCL version ..." banner goes to stdout under NCCL_DEBUG=VERSION/INFO: keep stdout to the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=dev)
 
     from mca_paper_b200 import config as C, ops, synthetic as S
@@ -609,7 +627,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu_base, "eager_gpu_baseline": eager_gpu, "fp32_parity_mode": fp32_mode, "final_loss": final_loss,
             "per_kernel_ms_per_step": {k: round(v["ms_total_per_step"], 4) for k, v in list(per_kernel.items())[:16]} if per_kernel else None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         eng.check_p2p()  # raises if a peer GPU missed one of the flag barriers (would invalidate the number)
         torch.distributed.barrier()
