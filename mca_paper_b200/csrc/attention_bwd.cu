@@ -714,15 +714,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
 }
 
-// delta[b,h,n] = sum_c dO*O ; ucorr[b, h*64+c] += dO[row, h*64+c] / N for rows whose lse is +inf (fully masked).
+// delta[b,h,n] = sum_c dO*O ; ucorr[b, h*64+c] += dO[row, h*64+c] / N for rows whose lse is +inf (fully masked); dq_zero[row] = 0.
 // Block (x, b) walks 16 rows of sample b (two per warp: 320 blocks of 64 rows left the HBM pipe half empty); the masked rows' dO are summed in registers, then across the 8 warps in shared
 // memory, and only then added to ucorr — one atomic per column and block instead of one per column and row (with 40 %
 // modality dropout a third of all rows are fully masked and the per-row atomics on 4096 addresses dominated the step).
 constexpr int PREP_ROWS = 16;
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                     const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ ucorr, int B, int N,
-                     int H) {
+                     const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ ucorr,
+                     float* __restrict__ dq_zero, int B, int N, int H) {
   __shared__ float s_part[8][512];
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -739,6 +739,11 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16*
     const long long row = static_cast<long long>(b) * N + n;
     const uint4* o4 = reinterpret_cast<const uint4*>(out + row * HD + c0);
     const uint4* d4 = reinterpret_cast<const uint4*>(dout + row * HD + c0);
+    // the fp32 dQ accumulator of this row is cleared here (the main kernel reduce-adds into it): one pass over the rows
+    // instead of a separate 42 MB memset in front of it
+    float4* z4 = reinterpret_cast<float4*>(dq_zero + row * HD + c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float dv[16];
     float acc = 0.f;
 #pragma unroll
@@ -802,10 +807,10 @@ extern "C" int mca_attn_bwd(const void* qkv, const void* out, const void* dout, 
       return MCA_ERR_CUDA;
     attr = true;
   }
-  if (cudaMemsetAsync(dq_accum, 0, M * HD * sizeof(float), stream) != cudaSuccess) return MCA_ERR_CUDA;
   if (cudaMemsetAsync(ucorr, 0, static_cast<size_t>(B) * HD * sizeof(float), stream) != cudaSuccess) return MCA_ERR_CUDA;
   attn_bwd_prep_kernel<<<dim3((N + PREP_ROWS - 1) / PREP_ROWS, B), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta, ucorr, B, N, H);
+      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta, ucorr, dq_accum, B,
+      N, H);
   const int n_items = B * H * n_kt;  // item index = key tile (slow) x (sample, head)
   AttnBwdArgs a{k_tiles_q, qt_list, q_tiles, rowbits, keygrp, tile_grp, padding, kt_class, skip_ok, lse, delta, ucorr,
                 reinterpret_cast<__nv_bfloat16*>(dqkv), N, H, n_kt, n_items, B * H};
