@@ -137,24 +137,38 @@ tabular_split_kernel(const float* __restrict__ values, const float* __restrict__
 __global__ void __launch_bounds__(256)
 geglu_f32_kernel(const float* __restrict__ u32, __nv_bfloat16* __restrict__ h3, __nv_bfloat16* __restrict__ h16,
                  __nv_bfloat16* __restrict__ u16, long long M, int IP) {
-  const long long n = M * IP;
+  const int q4 = IP / 4;  // thread = four consecutive h columns (they never straddle a 64-column block)
+  const long long n = M * q4;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / IP;
-    const int c = static_cast<int>(i % IP);
+    const long long r = i / q4;
+    const int c = static_cast<int>(i % q4) * 4;
     const int blk = c >> 6, j = c & 63;
-    const float x = u32[r * (2LL * IP) + blk * 128 + j], g = u32[r * (2LL * IP) + blk * 128 + 64 + j];
-    const float cdf = 0.5f * (1.0f + erff(g * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * expf(-0.5f * g * g);
-    const float ge = g * cdf;
-    const float h = x * ge;
-    __nv_bfloat16 hh, hl;
-    split2(h, hh, hl);
-    __nv_bfloat16* o = h3 + r * (3LL * IP);
-    o[c] = hh, o[IP + c] = hh, o[2 * IP + c] = hl;
-    h16[r * IP + c] = hh;
-    u16[r * (2LL * IP) + blk * 128 + j] = __float2bfloat16_rn(ge);
-    u16[r * (2LL * IP) + blk * 128 + 64 + j] = __float2bfloat16_rn(x * fmaf(g, pdf, cdf));
+    const float4 xv = *reinterpret_cast<const float4*>(u32 + r * (2LL * IP) + blk * 128 + j);
+    const float4 gv = *reinterpret_cast<const float4*>(u32 + r * (2LL * IP) + blk * 128 + 64 + j);
+    const float x[4] = {xv.x, xv.y, xv.z, xv.w}, g[4] = {gv.x, gv.y, gv.z, gv.w};
+    float hh[4], hl[4], av[4], bv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float cdf = 0.5f * (1.0f + erff(g[k] * 0.70710678118654752f));
+      const float pdf = 0.3989422804014327f * expf(-0.5f * g[k] * g[k]);
+      const float ge = g[k] * cdf;
+      const float h = x[k] * ge;
+      __nv_bfloat16 bh, bl;
+      split2(h, bh, bl);
+      hh[k] = __bfloat162float(bh), hl[k] = __bfloat162float(bl);
+      av[k] = ge, bv[k] = x[k] * fmaf(g[k], pdf, cdf);
+    }
+    const uint2 whi = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
+    const uint2 wlo = make_uint2(pack_bf16x2(hl[0], hl[1]), pack_bf16x2(hl[2], hl[3]));
+    __nv_bfloat16* o = h3 + r * (3LL * IP) + c;
+    *reinterpret_cast<uint2*>(o) = whi;
+    *reinterpret_cast<uint2*>(o + IP) = whi;
+    *reinterpret_cast<uint2*>(o + 2 * IP) = wlo;
+    *reinterpret_cast<uint2*>(h16 + r * IP + c) = whi;
+    *reinterpret_cast<uint2*>(u16 + r * (2LL * IP) + blk * 128 + j) = make_uint2(pack_bf16x2(av[0], av[1]), pack_bf16x2(av[2], av[3]));
+    *reinterpret_cast<uint2*>(u16 + r * (2LL * IP) + blk * 128 + 64 + j) =
+        make_uint2(pack_bf16x2(bv[0], bv[1]), pack_bf16x2(bv[2], bv[3]));
   }
 }
 
