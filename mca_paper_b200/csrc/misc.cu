@@ -106,28 +106,62 @@ __device__ __forceinline__ int map_row(const mca_pack_desc& d, int r) {
   return d.dst_row0 + (v / 64) * 128 + gate * 64 + (v % 64);
 }
 
-// one warp per source row (no per-element division; loads coalesced along the row), grid.y = descriptor
+// one warp per source row (no per-element division; loads coalesced along the row), grid.y = descriptor; rows whose width is
+// a multiple of 4 move as float4 -> 4 x bf16 (every matrix but the 713- / 35- / 74-wide encoder projections)
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ arena,
                     const mca_pack_desc* __restrict__ descs) {
   const mca_pack_desc d = descs[blockIdx.y];
   const int lane = threadIdx.x & 31;
+  const bool vec = (d.cols & 3) == 0 && (d.src_off & 3) == 0 && (d.dst_off & 3) == 0 && (d.dst_ld & 3) == 0;
   for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < d.rows; r += gridDim.x * 8) {
     const float* src = params + d.src_off + static_cast<long long>(r) * d.cols;
     __nv_bfloat16* dst = arena + d.dst_off + static_cast<long long>(map_row(d, r)) * d.dst_ld;
-    for (int c = lane; c < d.cols; c += 32) dst[c] = __float2bfloat16(src[c] * d.scale);
+    if (vec) {
+      for (int c = lane * 4; c < d.cols; c += 128) {
+        const float4 q = *reinterpret_cast<const float4*>(src + c);
+        *reinterpret_cast<uint2*>(dst + c) =
+            make_uint2(pack_bf16x2(q.x * d.scale, q.y * d.scale), pack_bf16x2(q.z * d.scale, q.w * d.scale));
+      }
+    } else {
+      for (int c = lane; c < d.cols; c += 32) dst[c] = __float2bfloat16(src[c] * d.scale);
+    }
   }
 }
 
-// grads[row] = scale * sum over the n_splits slabs (warp per row, four independent row segments in flight per lane)
+// grads[row] = scale * sum over the n_splits slabs (warp per row; float4 lanes with four independent row segments in flight
+// when the row width allows it)
 __global__ void __launch_bounds__(256)
 unpack_grads_kernel(float* __restrict__ grads, const float* __restrict__ partials,
                     const mca_pack_desc* __restrict__ descs) {
   const mca_pack_desc d = descs[blockIdx.y];
   const int lane = threadIdx.x & 31;
+  const bool vec = (d.cols & 3) == 0 && (d.src_off & 3) == 0 && (d.dst_off & 3) == 0 && (d.dst_ld & 3) == 0 &&
+                   (d.split_stride & 3) == 0;
   for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < d.rows; r += gridDim.x * 8) {
     float* dst = grads + d.src_off + static_cast<long long>(r) * d.cols;
     const float* p = partials + d.dst_off + static_cast<long long>(map_row(d, r)) * d.dst_ld;
+    if (vec) {
+      for (int c0 = lane * 4; c0 < d.cols; c0 += 512) {
+        float4 acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < d.n_splits; ++z) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (c0 + 128 * u < d.cols) {
+              const float4 q = *reinterpret_cast<const float4*>(p + static_cast<long long>(z) * d.split_stride + c0 + 128 * u);
+              acc[u].x += q.x, acc[u].y += q.y, acc[u].z += q.z, acc[u].w += q.w;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c0 + 128 * u < d.cols)
+            *reinterpret_cast<float4*>(dst + c0 + 128 * u) =
+                make_float4(acc[u].x * d.scale, acc[u].y * d.scale, acc[u].z * d.scale, acc[u].w * d.scale);
+      }
+      continue;
+    }
     for (int c0 = lane; c0 < d.cols; c0 += 128) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int z = 0; z < d.n_splits; ++z) {
