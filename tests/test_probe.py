@@ -52,6 +52,23 @@ def test_probe_host_logic_consumes_rng_like_the_reference():
         LinearProbe(FineTuneDataset(e_tr, s_tr), FineTuneDataset(e_ev, s_ev), device="cpu", loss_type="huber")
 
 
+@pytest.mark.parametrize("sched", ["cosine", "linear", "constant_with_warmup", "constant"])
+def test_probe_lr_schedule_matches_transformers(sched):
+    """lr_at(k) (host mirror of the schedule inside mca_probe_epoch) == the rate transformers.get_scheduler gives the k-th
+    optimiser step (lp_accel_gpu.py:161-167: scheduler.step() after every optimizer.step())."""
+    from transformers import get_scheduler
+    e_tr, s_tr, e_ev, s_ev = _data(n_train=200, n_eval=50)
+    cfg = dict(CFG, lr_scheduler_type=sched, epochs=5, num_warmup_steps=4, lr=3e-3)
+    probe = LinearProbe(FineTuneDataset(e_tr, s_tr, index=0), FineTuneDataset(e_ev, s_ev, index=0), device="cpu", **cfg)
+    total = cfg["epochs"] * len(probe.train_dl)
+    opt = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=cfg["lr"])
+    sch = get_scheduler(name=sched, optimizer=opt, num_warmup_steps=4, num_training_steps=total)
+    for k in range(1, total + 1):
+        assert abs(probe.lr_at(k) - opt.param_groups[0]["lr"]) <= 1e-9 + 1e-6 * cfg["lr"], (sched, k)
+        opt.step()
+        sch.step()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("loss_type,task,sched", [("L1", 0, "cosine"), ("MSE", 2, "linear"), ("MSE", -1, "constant_with_warmup"),
                                                   ("BCE", 1, "cosine"), ("CE", -1, "constant")])
